@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py — MSDeformAttn fwd+bwd throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+Workloads (all M=8, D=32, L=4, P=4, synthetic tensors, DINO 4-scale R50 800x1333 pyramid):
+  encoder6   (default; BASELINE configs[1]) six deformable-encoder layers' MSDeformAttn, bs=2 per GPU,
+             Lq=S=22,223, fp32, encoder-realistic locations "E"; one step = 6 forwards then 6 backwards
+             on six distinct input sets (960 MB > L2, so no layer finds its inputs cached).
+  decoder6   (configs[2]) six decoder cross-attention layers, bs=2, Lq=1100, bf16 value, locations "Dn".
+  encoder1_hr1333 / encoder1_hr2000   (configs[4]) one encoder layer at 1333x1333 / 1600x2000.
+Add --deterministic for the sort-by-corner grad_value mode.
+
+One process per GPU (torchrun for N>1); the op never communicates (images are independent), so ranks
+only meet at the barriers around the timed region; value = queries processed by all ranks / max-over-ranks
+device time.  Prints ONE JSON line on rank 0.
+
+--impl reference times the reference's CPU path for this op — ms_deform_attn_core_pytorch (grid_sample)
+forward + autograd backward, restated in oracle/msda_oracle.py because /root/reference does not travel to
+the GPU box — on the host cores, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "MSDeformAttn fwd+bwd queries/s & % memory roofline, DINO 4-scale R50 800x1333"
+UNIT = "queries/s"
+
+WORKLOADS = {
+    # name: (image hw, layers, batch/GPU, kind, Lq (None = S), value dtype)
+    "encoder6": ((800, 1333), 6, 2, "E", None, "f32"),
+    "encoder1": ((800, 1333), 1, 2, "E", None, "f32"),
+    "decoder6": ((800, 1333), 6, 2, "Dn", 1100, "bf16"),
+    "decoder6_f32": ((800, 1333), 6, 2, "Dn", 1100, "f32"),
+    "encoder1_hr1333": ((1333, 1333), 1, 2, "E", None, "f32"),
+    "encoder1_hr2000": ((1600, 2000), 1, 2, "E", None, "f32"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="encoder6", choices=sorted(WORKLOADS))
+    ap.add_argument("--deterministic", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background during the timed region)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's CPU path (grid_sample), bounded sample
+# --------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, hw=(800, 1333)):
+    """One step = one encoder layer, bs=1, fp32, fwd + autograd bwd (BASELINE configs[0]) on all host cores."""
+    import torch
+
+    from oracle.msda_oracle import core_pytorch_fwd_bwd
+    from richsem_b200 import synthetic as syn
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    shapes = syn.level_shapes(*hw)
+    i = syn.make_inputs("E", 1, shapes, "cpu", seed=1234)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        core_pytorch_fwd_bwd(i["value"], shapes, i["loc"], i["attw"], i["grad_out"])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    qps = steps * i["Lq"] / total
+    return dict(value=qps, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"{steps} x (one encoder layer, bs=1, Lq=S={i['Lq']}, fp32, fwd+autograd bwd of the "
+                       f"grid_sample formulation), {warmup} warm-up, {total:.1f} s timed",
+                ms_per_step=1e3 * total / steps)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    hw, layers, bs, kind, lq, vdt = WORKLOADS[args.workload]
+    r = cpu_reference_run(steps, warmup, hw if kind == "E" else (800, 1333))
+    line = {
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "note": "CPU path of the reference op (grid_sample formulation), "
+                   "one encoder layer bs=1 per step, host cores only"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import richsem_b200
+    from richsem_b200 import MultiScaleDeformableAttention as ext
+    from richsem_b200 import _capi, synthetic as syn
+
+    hw, layers, bs, kind, lq, vdt = WORKLOADS[args.workload]
+    shapes = syn.level_shapes(*hw)
+    tdt = torch.bfloat16 if vdt == "bf16" else torch.float32
+    sets = [syn.make_inputs(kind, bs, shapes, dev, seed=1234 + 100 * rank + i, lq=lq, dtype=tdt) for i in range(layers)]
+    S, Lq = sets[0]["S"], sets[0]["Lq"]
+    shp, st = sets[0]["shapes"], sets[0]["starts"]
+    queries_per_step = layers * bs * Lq
+    flags = _capi.FLAG_DETERMINISTIC if args.deterministic else 0
+    vb = 2 if vdt == "bf16" else 4
+    fwd_bytes, bwd_bytes = syn.algorithmic_bytes(bs, S, Lq, value_bytes=vb, out_bytes=vb)
+    in_bytes = sum(s[k].numel() * s[k].element_size() for s in sets for k in ("value", "loc", "attw", "grad_out"))
+
+    def step(timing=None):
+        for i, s in enumerate(sets):
+            if timing is not None:
+                timing["f0"][i].record()
+            s["out"] = ext.ms_deform_attn_forward(s["value"], shp, st, s["loc"], s["attw"], 64)
+            if timing is not None:
+                timing["f1"][i].record()
+        for i in reversed(range(layers)):
+            s = sets[i]
+            if timing is not None:
+                timing["b0"][i].record()
+            s["grads"] = ext.ms_deform_attn_backward(s["value"], shp, st, s["loc"], s["attw"], s["grad_out"], 64,
+                                                     _flags=flags)
+            if timing is not None:
+                timing["b1"][i].record()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    timings = [{k: [ev() for _ in range(layers)] for k in ("f0", "f1", "b0", "b1")} for _ in range(args.steps)]
+    start, stop = ev(), ev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    launches0 = _capi.launch_count()
+    sync_all()
+    start.record()
+    for k in range(args.steps):
+        step(timings[k])
+    stop.record()
+    sync_all()
+    launches = _capi.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = start.elapsed_time(stop)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = world * queries_per_step / (ms_per_step * 1e-3)
+
+    fwd_ms = statistics.mean(tm["f0"][i].elapsed_time(tm["f1"][i]) for tm in timings for i in range(layers))
+    bwd_ms = statistics.mean(tm["b0"][i].elapsed_time(tm["b1"][i]) for tm in timings for i in range(layers))
+    peak, peak_src = peaks()
+
+    # ---- e2e: the same step through the public API with HOST buffers ------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, dist, ext, sets, shp, st, flags, world, dev, queries_per_step)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(steps=4, warmup=1)
+        cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    dom = "backward" if bwd_ms >= fwd_ms else "forward"
+    dom_bytes, dom_ms = (bwd_bytes, bwd_ms) if dom == "backward" else (fwd_bytes, fwd_ms)
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": vdt, "data": "synthetic",
+        "config": {"workload": args.workload, "image": f"{hw[0]}x{hw[1]}", "levels": shapes, "S": S, "Lq": Lq,
+                   "batch_per_gpu": bs, "layers_per_step": layers, "heads": 8, "head_dim": 32, "points": 4,
+                   "locations": kind, "grad_value_mode": "deterministic" if args.deterministic else "atomic",
+                   "parallelism": f"batch-sharded x{world}, no collective in the op",
+                   "l2_policy": f"{layers} distinct input sets per step ({in_bytes / 1e6:.0f} MB of inputs) "
+                                "larger than the 126 MB L2; no explicit flush"},
+        "roofline": {"bound": "hbm", "kernel": f"msda {dom} ({'memset + ' if dom == 'backward' else ''}kernel), avg of "
+                     f"{args.steps * layers} launches", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms},
+        "roofline_fwd_bwd": {"achieved": (fwd_bytes + bwd_bytes) * layers / (ms_per_step * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": (fwd_bytes + bwd_bytes) * layers / (ms_per_step * 1e-3) / 1e9 / peak,
+                             "fwd_ms_per_layer": fwd_ms, "bwd_ms_per_layer": bwd_ms,
+                             "fwd_GBps": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "bwd_GBps": bwd_bytes / (bwd_ms * 1e-3) / 1e9,
+                             "bytes_per_query": (fwd_bytes + bwd_bytes) / (bs * Lq)},
+        "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "lib": _capi.build_info(),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, dist, ext, sets, shp, st, flags, world, dev, queries_per_step):
+    """Host buffers in, host buffers out: per step every layer's value / locations / weights / grad_out
+    are copied from pinned host memory, and the output and the three gradients are copied back.
+    Copies run on their own streams so that transfers of neighbouring layers overlap the kernels."""
+    layers = len(sets)
+    names_in = ("value", "loc", "attw", "grad_out")
+    host_in = [{k: s[k].cpu().pin_memory() for k in names_in} for s in sets]
+    dev_in = [{k: torch.empty_like(s[k]) for k in names_in} for s in sets]
+    host_out = None
+    h2d, d2h, comp = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
+    h2d_bytes = sum(t.numel() * t.element_size() for hi in host_in for t in hi.values())
+
+    def e2e_step():
+        nonlocal host_out
+        ev_in = []
+        h2d.wait_stream(comp)  # the previous step's kernels still read the device input buffers
+        with torch.cuda.stream(h2d):
+            for i in range(layers):
+                for k in names_in:
+                    dev_in[i][k].copy_(host_in[i][k], non_blocking=True)
+                e = torch.cuda.Event(); e.record(h2d); ev_in.append(e)
+        outs, grads = [None] * layers, [None] * layers
+        ev_f, ev_b = [], [None] * layers
+        for i in range(layers):
+            comp.wait_event(ev_in[i])
+            outs[i] = ext.ms_deform_attn_forward(dev_in[i]["value"], shp, st, dev_in[i]["loc"], dev_in[i]["attw"], 64)
+            e = torch.cuda.Event(); e.record(comp); ev_f.append(e)
+        for i in reversed(range(layers)):
+            grads[i] = ext.ms_deform_attn_backward(dev_in[i]["value"], shp, st, dev_in[i]["loc"], dev_in[i]["attw"],
+                                                   dev_in[i]["grad_out"], 64, _flags=flags)
+            e = torch.cuda.Event(); e.record(comp); ev_b[i] = e
+        if host_out is None:
+            host_out = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (outs[i], *grads[i])]
+                        for i in range(layers)]
+        with torch.cuda.stream(d2h):
+            for i in range(layers):
+                d2h.wait_event(ev_f[i])
+                host_out[i][0].copy_(outs[i], non_blocking=True)
+            for i in reversed(range(layers)):
+                d2h.wait_event(ev_b[i])
+                for j in range(3):
+                    host_out[i][1 + j].copy_(grads[i][j], non_blocking=True)
+        comp.wait_stream(d2h)
+        for i in range(layers):  # keep device results alive until the copies are ordered after them
+            for t in (outs[i], *grads[i]):
+                t.record_stream(d2h)
+
+    for _ in range(2):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.e2e_steps
+    d2h_bytes = sum(t.numel() * t.element_size() for ho in host_out for t in ho)
+    return {"value": world * queries_per_step / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+            "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms, "steps": args.e2e_steps,
+            "note": "pinned host buffers -> H2D -> fwd/bwd through the drop-in API -> D2H of out + 3 grads, copies on side streams"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,163 @@
+/*
+ * msda_b200.h — C ABI of libmsda_b200.so: multi-scale deformable attention
+ * (MSDeformAttn) forward / backward for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for RichSem's native extension
+ * `MultiScaleDeformableAttention` (reference: models/richsem/ops/src/).  Every
+ * entry point replaces one templated launcher of the reference and keeps its
+ * argument order; the trailing `const msda_opts*` is the only addition and may
+ * be NULL.
+ *
+ *   msda_forward_{f32,f64,bf16}   <-  ms_deformable_im2col_cuda<scalar_t>
+ *                                     (models/richsem/ops/src/cuda/ms_deform_im2col_cuda.cuh:923-954)
+ *   msda_backward_{f32,f64,bf16}  <-  ms_deformable_col2im_cuda<scalar_t>
+ *                                     (models/richsem/ops/src/cuda/ms_deform_im2col_cuda.cuh:956-1327)
+ *
+ * Tensor layouts (all contiguous, exactly the reference's,
+ * models/richsem/ops/src/cuda/ms_deform_attn_cuda.cu:40-48):
+ *   value              [batch, spatial_size, num_heads, channels]
+ *   spatial_shapes     [num_levels, 2]  int64, rows are (H_l, W_l)
+ *   level_start_index  [num_levels]     int64
+ *   sampling_loc       [batch, num_query, num_heads, num_levels, num_point, 2]  (x, y) in [0,1]
+ *   attn_weight        [batch, num_query, num_heads, num_levels, num_point]
+ *   out / grad_out     [batch, num_query, num_heads * channels]
+ *
+ * Differences from the reference launchers, all deliberate:
+ *   - every function returns a status (the reference printf()s launch errors
+ *     and carries on, cuh:948-952, 1321-1325);
+ *   - one launch covers the whole batch: `im2col_step` chunking
+ *     (ms_deform_attn_cuda.cu:50-75) is a host-side loop over independent
+ *     images and is validated by the host wrapper only;
+ *   - the backward zero-fills grad_value itself (the reference relies on
+ *     at::zeros_like, ms_deform_attn_cuda.cu:121-123) unless
+ *     MSDA_FLAG_GRAD_VALUE_PREZEROED is set; grad_sampling_loc and
+ *     grad_attn_weight are fully overwritten;
+ *   - the per-level table travels to the kernels in kernel-parameter constant
+ *     memory, so the library needs the table on the host.  `spatial_shapes`
+ *     and `level_start_index` stay DEVICE pointers as in the reference; pass a
+ *     host mirror in msda_opts to avoid a blocking device->host copy (required
+ *     under CUDA-graph capture).
+ *
+ * No function allocates device memory, synchronises the device (except the
+ * mirror-less path noted above) or retains any pointer after it returns.
+ * All work is enqueued on `stream`.  Thread-safe and re-entrant.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_ABI_VERSION 1
+#define MSDA_MAX_LEVELS 16
+
+/* status codes */
+#define MSDA_OK 0
+#define MSDA_ERR_INVALID_ARGUMENT 1 /* bad pointer / dimension / alignment        */
+#define MSDA_ERR_UNSUPPORTED 2      /* shape outside what the library implements */
+#define MSDA_ERR_CUDA 3             /* a CUDA runtime call or launch failed       */
+#define MSDA_ERR_WORKSPACE 4        /* deterministic mode: workspace missing/small */
+
+/* msda_opts.flags */
+#define MSDA_FLAG_DETERMINISTIC 0x1u          /* grad_value via sort-by-corner segmented sum, bitwise reproducible */
+#define MSDA_FLAG_GRAD_VALUE_PREZEROED 0x2u   /* caller already zeroed grad_value (or wants accumulation)           */
+#define MSDA_FLAG_FORCE_GENERIC 0x4u          /* bypass the D=32 fast kernels (testing)                             */
+
+typedef void* msda_stream_t; /* cudaStream_t */
+
+typedef struct msda_opts {
+  uint32_t struct_size;                   /* sizeof(msda_opts); lets the struct grow */
+  uint32_t flags;
+  const int64_t* spatial_shapes_host;     /* optional host mirror of spatial_shapes [num_levels*2]   */
+  const int64_t* level_start_index_host;  /* optional host mirror of level_start_index [num_levels]  */
+  /* Optional processing order of the queries (DEVICE int32 array).  Entry i is a
+   * query index in [0, num_query) or -1 (skip).  Every query must appear exactly
+   * once.  It only changes which thread block handles which query, i.e. cache
+   * locality, never results.  NULL = natural order. */
+  const int32_t* query_order;
+  int32_t query_order_len;
+  int32_t reserved0;
+  void* workspace;                        /* DEVICE scratch for MSDA_FLAG_DETERMINISTIC */
+  size_t workspace_bytes;
+} msda_opts;
+
+/* ---- forward --------------------------------------------------------------
+ * out[b,q,m,:] = sum_{l,p} attn_weight[b,q,m,l,p] * bilinear(value_l[b,:,m,:]; x*W_l-0.5, y*H_l-0.5)
+ * zero padding; semantics of cuh:237-299 + cuh:33-84. */
+int msda_forward_f32(msda_stream_t stream, const float* value, const int64_t* spatial_shapes,
+                     const int64_t* level_start_index, const float* sampling_loc,
+                     const float* attn_weight, int batch, int spatial_size, int num_heads,
+                     int channels, int num_levels, int num_query, int num_point, float* out,
+                     const msda_opts* opts);
+int msda_forward_f64(msda_stream_t stream, const double* value, const int64_t* spatial_shapes,
+                     const int64_t* level_start_index, const double* sampling_loc,
+                     const double* attn_weight, int batch, int spatial_size, int num_heads,
+                     int channels, int num_levels, int num_query, int num_point, double* out,
+                     const msda_opts* opts);
+/* bf16 variant (new capability, no reference counterpart): value and out are
+ * bfloat16 bit patterns (uint16_t); sampling_loc / attn_weight stay fp32;
+ * accumulation is fp32. */
+int msda_forward_bf16(msda_stream_t stream, const uint16_t* value, const int64_t* spatial_shapes,
+                      const int64_t* level_start_index, const float* sampling_loc,
+                      const float* attn_weight, int batch, int spatial_size, int num_heads,
+                      int channels, int num_levels, int num_query, int num_point, uint16_t* out,
+                      const msda_opts* opts);
+
+/* ---- backward -------------------------------------------------------------
+ * gradient formulas of cuh:87-159; argument order of cuh:956-973. */
+int msda_backward_f32(msda_stream_t stream, const float* grad_out, const float* value,
+                      const int64_t* spatial_shapes, const int64_t* level_start_index,
+                      const float* sampling_loc, const float* attn_weight, int batch,
+                      int spatial_size, int num_heads, int channels, int num_levels,
+                      int num_query, int num_point, float* grad_value, float* grad_sampling_loc,
+                      float* grad_attn_weight, const msda_opts* opts);
+int msda_backward_f64(msda_stream_t stream, const double* grad_out, const double* value,
+                      const int64_t* spatial_shapes, const int64_t* level_start_index,
+                      const double* sampling_loc, const double* attn_weight, int batch,
+                      int spatial_size, int num_heads, int channels, int num_levels,
+                      int num_query, int num_point, double* grad_value, double* grad_sampling_loc,
+                      double* grad_attn_weight, const msda_opts* opts);
+/* bf16 variant: grad_out and value are bfloat16; all three gradients are fp32. */
+int msda_backward_bf16(msda_stream_t stream, const uint16_t* grad_out, const uint16_t* value,
+                       const int64_t* spatial_shapes, const int64_t* level_start_index,
+                       const float* sampling_loc, const float* attn_weight, int batch,
+                       int spatial_size, int num_heads, int channels, int num_levels,
+                       int num_query, int num_point, float* grad_value, float* grad_sampling_loc,
+                       float* grad_attn_weight, const msda_opts* opts);
+
+/* ---- index contract probe --------------------------------------------------
+ * Writes, for every sample (b,q,m,l,p), the four bilinear corner token indices
+ * (level_start_index[l] + h*W_l + w, i.e. an index into the spatial_size axis)
+ * in the order (h0,w0) (h0,w1) (h1,w0) (h1,w1); -1 for a corner that
+ * contributes nothing (out of the map, or the whole sample skipped by the range
+ * test of cuh:288).  corners: int32 [batch,num_query,num_heads,num_levels,num_point,4].
+ * Uses the same device function as the production fp32/bf16 kernels. */
+int msda_debug_corners_f32(msda_stream_t stream, const int64_t* spatial_shapes,
+                           const int64_t* level_start_index, const float* sampling_loc, int batch,
+                           int num_heads, int num_levels, int num_query, int num_point,
+                           int32_t* corners, const msda_opts* opts);
+
+/* ---- misc ------------------------------------------------------------------ */
+/* Bytes of device workspace MSDA_FLAG_DETERMINISTIC needs for this problem. */
+size_t msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels,
+                                     int num_levels, int num_query, int num_point);
+/* 1 if (dtype_bytes, channels, num_levels, num_point) is served by the tuned kernels, else 0
+ * (the generic kernels serve everything else). dtype_bytes: 4 = f32, 8 = f64, 2 = bf16. */
+int msda_has_fast_path(int dtype_bytes, int channels, int num_levels, int num_point);
+int msda_abi_version(void);
+/* Static build description: "msda_b200 <abi> sm_100a <date>". */
+const char* msda_build_info(void);
+/* Message for the last non-OK status returned on the calling thread. */
+const char* msda_last_error(void);
+/* Number of kernels this library has launched since load (all threads); used by bench.py
+ * for its gpu_launches figure. */
+uint64_t msda_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

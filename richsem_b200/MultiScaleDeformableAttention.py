@@ -1,0 +1,163 @@
+"""Drop-in for RichSem's compiled extension module ``MultiScaleDeformableAttention``.
+
+Same two entry points, argument order and return types as the pybind11 module of the reference
+(/root/reference/models/richsem/ops/src/vision.cpp:13-16, prototypes ms_deform_attn.h:20-27,41-49,
+host wrappers cuda/ms_deform_attn_cuda.cu:20-80 and :83-153), implemented on top of the C ABI of
+libmsda_b200.so.  To use it under the reference's import name::
+
+    import sys, richsem_b200.MultiScaleDeformableAttention as m
+    sys.modules["MultiScaleDeformableAttention"] = m
+
+Error behaviour mirrors the reference: precondition failures raise RuntimeError (the reference's
+AT_ASSERTM); CPU tensors raise "Not implemented on the CPU" (ms_deform_attn.h:38).  Kernel launch
+failures also raise (the reference only printf()s them).
+
+Beyond the reference: bfloat16 ``value`` (fp32 locations / weights, bf16 output, fp32 gradients),
+and a deterministic grad_value mode (see ``set_deterministic``).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _capi
+
+_SUFFIX = {torch.float32: "f32", torch.float64: "f64", torch.bfloat16: "bf16"}
+_state = {"deterministic": os.environ.get("MSDA_B200_DETERMINISTIC", "0") not in ("", "0")}
+_workspaces: dict = {}
+
+
+def set_deterministic(flag: bool) -> None:
+    """grad_value by sort-by-corner segmented sums (bitwise reproducible) instead of fp32 atomics."""
+    _state["deterministic"] = bool(flag)
+
+
+def is_deterministic() -> bool:
+    return _state["deterministic"] or torch.are_deterministic_algorithms_enabled()
+
+
+def _require(cond: bool, msg: str) -> None:
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _check_inputs(named):
+    for name, t in named:
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+    for name, t in named:
+        if not t.is_cuda:
+            if name == "value":
+                raise RuntimeError("Not implemented on the CPU")
+            if name not in ("spatial_shapes", "level_start_index"):
+                raise RuntimeError(f"{name} must be a CUDA tensor")
+
+
+def _dims(value, spatial_shapes, sampling_loc, attn_weight, im2col_step):
+    _require(value.dim() == 4, "value must be (N, S, M, D)")
+    _require(sampling_loc.dim() == 6 and sampling_loc.shape[-1] == 2, "sampling_loc must be (N, Lq, M, L, P, 2)")
+    batch, spatial_size, num_heads, channels = value.shape
+    num_levels = spatial_shapes.shape[0]
+    num_query, num_point = sampling_loc.shape[1], sampling_loc.shape[4]
+    _require(tuple(sampling_loc.shape) == (batch, num_query, num_heads, num_levels, num_point, 2),
+             "sampling_loc shape does not match value / spatial_shapes")
+    _require(tuple(attn_weight.shape) == (batch, num_query, num_heads, num_levels, num_point),
+             "attn_weight shape does not match sampling_loc")
+    # The reference splits the batch into chunks of min(batch, im2col_step) images and launches once
+    # per chunk (ms_deform_attn_cuda.cu:50-75); images are independent, so one launch covers them
+    # all here, but the divisibility requirement is kept so that callers see the same errors.
+    step = min(batch, int(im2col_step)) if batch > 0 else 1
+    _require(step > 0 and batch % step == 0, f"batch({batch}) must divide im2col_step({step})")
+    return batch, spatial_size, num_heads, channels, num_levels, num_query, num_point
+
+
+def _aux_dtype(value):
+    return torch.float32 if value.dtype == torch.bfloat16 else value.dtype
+
+
+def _suffix(value, sampling_loc, attn_weight):
+    sfx = _SUFFIX.get(value.dtype)
+    if sfx is None:
+        raise RuntimeError(f'"ms_deform_attn" not implemented for \'{value.dtype}\'')
+    aux = _aux_dtype(value)
+    _require(sampling_loc.dtype == aux and attn_weight.dtype == aux,
+             f"sampling_loc / attn_weight must be {aux} when value is {value.dtype}")
+    return sfx
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev_ptr(t):
+    return t.data_ptr() if t.is_cuda else None
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step,
+                           _flags: int = 0):
+    _check_inputs((("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)))
+    n, s, m, d, nl, lq, npt = _dims(value, spatial_shapes, sampling_loc, attn_weight, im2col_step)
+    sfx = _suffix(value, sampling_loc, attn_weight)
+    meta = _capi.level_meta(spatial_shapes, level_start_index)
+    out = torch.empty((n, lq, m * d), dtype=value.dtype, device=value.device)
+    opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=_flags)
+    with torch.cuda.device(value.device):
+        rc = getattr(_capi.lib, "msda_forward_" + sfx)(
+            _stream(), value.data_ptr(), _dev_ptr(spatial_shapes), _dev_ptr(level_start_index),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), n, s, m, d, nl, lq, npt, out.data_ptr(), opts)
+    _capi.check(rc, "msda_forward_" + sfx)
+    return out
+
+
+def _workspace(nbytes, device):
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.1) + 256, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step, _flags: int = 0):
+    _check_inputs((("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)))
+    n, s, m, d, nl, lq, npt = _dims(value, spatial_shapes, sampling_loc, attn_weight, im2col_step)
+    sfx = _suffix(value, sampling_loc, attn_weight)
+    _require(grad_output.dtype == value.dtype and grad_output.numel() == n * lq * m * d,
+             "grad_output must have value's dtype and shape (N, Lq, M*D)")
+    meta = _capi.level_meta(spatial_shapes, level_start_index)
+    aux = _aux_dtype(value)
+    grad_value = torch.empty(value.shape, dtype=aux, device=value.device)  # zero-filled by the library
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_attw = torch.empty_like(attn_weight)
+    flags, ws = _flags, None
+    if is_deterministic() and value.dtype != torch.float64:
+        flags |= _capi.FLAG_DETERMINISTIC
+    if flags & _capi.FLAG_DETERMINISTIC:
+        ws = _workspace(_capi.lib.msda_backward_workspace_bytes(n, s, m, d, nl, lq, npt), value.device)
+    opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=flags, workspace=ws)
+    with torch.cuda.device(value.device):
+        rc = getattr(_capi.lib, "msda_backward_" + sfx)(
+            _stream(), grad_output.data_ptr(), value.data_ptr(), _dev_ptr(spatial_shapes),
+            _dev_ptr(level_start_index), sampling_loc.data_ptr(), attn_weight.data_ptr(), n, s, m, d, nl, lq, npt,
+            grad_value.data_ptr(), grad_loc.data_ptr(), grad_attw.data_ptr(), opts)
+    _capi.check(rc, "msda_backward_" + sfx)
+    return [grad_value, grad_loc, grad_attw]
+
+
+def debug_corners(spatial_shapes, level_start_index, sampling_loc):
+    """int32 (N,Lq,M,L,P,4) bilinear corner token indices as the fp32/bf16 kernels compute them
+    (-1 = contributes nothing).  Test hook for the bit-exact index contract."""
+    _require(sampling_loc.is_cuda and sampling_loc.dtype == torch.float32 and sampling_loc.is_contiguous(),
+             "sampling_loc must be a contiguous CUDA float32 tensor")
+    n, lq, m, nl, npt, _ = sampling_loc.shape
+    meta = _capi.level_meta(spatial_shapes, level_start_index)
+    out = torch.empty((n, lq, m, nl, npt, 4), dtype=torch.int32, device=sampling_loc.device)
+    with torch.cuda.device(sampling_loc.device):
+        rc = _capi.lib.msda_debug_corners_f32(_stream(), _dev_ptr(spatial_shapes), _dev_ptr(level_start_index),
+                                              sampling_loc.data_ptr(), n, m, nl, lq, npt, out.data_ptr(),
+                                              _capi.make_opts(meta))
+    _capi.check(rc, "msda_debug_corners_f32")
+    return out

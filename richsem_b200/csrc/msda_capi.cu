@@ -1,0 +1,399 @@
+// msda_capi.cu — extern "C" entry points of libmsda_b200.so (see include/msda_b200.h).
+// Validation, level-table resolution, kernel selection and launch.  No torch types.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "msda_host.h"
+#include "msda_bf16.cuh"
+#include "msda_d32.cuh"
+#include "msda_det.cuh"
+#include "msda_generic.cuh"
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+}  // namespace
+
+namespace msda {
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return MSDA_OK;
+  return fail(MSDA_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int after_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(cudaGetLastError(), what);
+}
+}  // namespace msda
+
+namespace {
+using msda::after_launch;
+using msda::check_cuda;
+using msda::fail;
+
+inline uint32_t opt_flags(const msda_opts* o) { return o ? o->flags : 0u; }
+
+struct Problem {
+  MsdaDims d;
+  MsdaLevels lv;
+  const int32_t* order;
+  int order_len;
+  uint32_t flags;
+};
+
+// Builds the constant-memory level table.  With a host mirror this is pure host work;
+// without one it is a blocking device->host copy on `stream` (documented slow path).
+int resolve_levels(cudaStream_t stream, const int64_t* shapes_dev, const int64_t* start_dev,
+                   int num_levels, int spatial_size, const msda_opts* opts, MsdaLevels* lv) {
+  if (num_levels < 1 || num_levels > MSDA_MAX_LEVELS)
+    return fail(MSDA_ERR_UNSUPPORTED, "num_levels=%d outside [1,%d]", num_levels, MSDA_MAX_LEVELS);
+  int64_t shp[2 * MSDA_MAX_LEVELS], st[MSDA_MAX_LEVELS];
+  if (opts && opts->spatial_shapes_host && opts->level_start_index_host) {
+    memcpy(shp, opts->spatial_shapes_host, sizeof(int64_t) * 2 * num_levels);
+    memcpy(st, opts->level_start_index_host, sizeof(int64_t) * num_levels);
+  } else {
+    if (!shapes_dev || !start_dev)
+      return fail(MSDA_ERR_INVALID_ARGUMENT, "spatial_shapes / level_start_index is NULL");
+    cudaError_t e = cudaMemcpyAsync(shp, shapes_dev, sizeof(int64_t) * 2 * num_levels,
+                                    cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(st, start_dev, sizeof(int64_t) * num_levels, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return check_cuda(e, "copy of the level table to the host");
+  }
+  memset(lv, 0, sizeof(*lv));
+  for (int l = 0; l < num_levels; ++l) {
+    const int64_t H = shp[2 * l], W = shp[2 * l + 1], s = st[l];
+    if (H < 1 || W < 1 || s < 0 || H > INT32_MAX || W > INT32_MAX || H * W > INT32_MAX ||
+        s + H * W > (int64_t)spatial_size)
+      return fail(MSDA_ERR_INVALID_ARGUMENT,
+                  "level %d: shape (%lld,%lld) start %lld does not fit spatial_size %d", l,
+                  (long long)H, (long long)W, (long long)s, spatial_size);
+    lv->H[l] = (int)H;
+    lv->W[l] = (int)W;
+    lv->start[l] = (int)s;
+  }
+  return MSDA_OK;
+}
+
+int make_problem(cudaStream_t stream, const int64_t* shapes, const int64_t* start, int batch,
+                 int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                 int num_point, const msda_opts* opts, Problem* pb) {
+  if (batch < 0 || spatial_size < 1 || num_heads < 1 || channels < 1 || num_query < 0 || num_point < 1)
+    return fail(MSDA_ERR_INVALID_ARGUMENT,
+                "bad dimensions: batch=%d spatial_size=%d num_heads=%d channels=%d num_levels=%d "
+                "num_query=%d num_point=%d",
+                batch, spatial_size, num_heads, channels, num_levels, num_query, num_point);
+  if (opts && opts->struct_size != sizeof(msda_opts))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_opts.struct_size=%u, library expects %zu",
+                opts->struct_size, sizeof(msda_opts));
+  pb->d = MsdaDims{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  pb->flags = opt_flags(opts);
+  pb->order = opts ? opts->query_order : nullptr;
+  pb->order_len = pb->order ? opts->query_order_len : num_query;
+  if (pb->order && pb->order_len < num_query)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "query_order_len=%d shorter than num_query=%d",
+                pb->order_len, num_query);
+  return resolve_levels(stream, shapes, start, num_levels, spatial_size, opts, &pb->lv);
+}
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+// lanes per value row in the tuned kernels: 8 -> LDG.128, 4 -> LDG.256
+int lanes_per_row() {
+  static const int g = [] {
+    const char* e = getenv("MSDA_B200_LANES_PER_ROW");
+    const int v = e ? atoi(e) : 0;
+    return (v == 4 || v == 8) ? v : 8;
+  }();
+  return g;
+}
+
+bool fast_shape(int dtype_bytes, int channels, int num_levels, int num_point) {
+  return (dtype_bytes == 4 || dtype_bytes == 2) && channels == 32 && num_point == 4 &&
+         num_levels >= 1 && num_levels <= 6;
+}
+
+bool fits_int32(const MsdaDims& d) {
+  return (long long)d.spatial_size * d.num_heads * d.channels < (1ll << 31);
+}
+
+int generic_grid(const MsdaDims& d) {
+  const long long tasks = (long long)d.batch * d.num_query * d.num_heads;
+  long long blocks = (tasks + 7) / 8;
+  if (blocks > 148ll * 64) blocks = 148ll * 64;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+// ---- tuned fp32 dispatch -------------------------------------------------------------------
+template <int G, int kL>
+int launch_fwd_d32(cudaStream_t s, const Problem& pb, const float* value, const float* loc,
+                   const float* attw, float* out) {
+  using Cfg = msda::D32Cfg<G, kL * 4>;
+  const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
+  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
+  msda::msda_fwd_d32_kernel<G, kL, 4><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
+      value, loc, attw, out, pb.order, pb.order_len, pb.lv, pb.d.spatial_size, pb.d.num_heads,
+      pb.d.num_query);
+  return after_launch("msda_fwd_d32_kernel");
+}
+template <int G, int kL, bool kScatter>
+int launch_bwd_d32(cudaStream_t s, const Problem& pb, const float* grad_out, const float* value,
+                   const float* loc, const float* attw, float* gv, float* gl, float* ga) {
+  using Cfg = msda::D32Cfg<G, kL * 4>;
+  const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
+  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
+  msda::msda_bwd_d32_kernel<G, kL, 4, kScatter><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
+      grad_out, value, loc, attw, gv, gl, ga, pb.order, pb.order_len, pb.lv, pb.d.spatial_size,
+      pb.d.num_heads, pb.d.num_query);
+  return after_launch("msda_bwd_d32_kernel");
+}
+
+#define MSDA_SWITCH_L(L_, CALL)                                                              \
+  switch (L_) {                                                                              \
+    case 1: return CALL(1);                                                                  \
+    case 2: return CALL(2);                                                                  \
+    case 3: return CALL(3);                                                                  \
+    case 4: return CALL(4);                                                                  \
+    case 5: return CALL(5);                                                                  \
+    case 6: return CALL(6);                                                                  \
+    default: return fail(MSDA_ERR_UNSUPPORTED, "no tuned kernel for num_levels=%d", L_);      \
+  }
+
+int fwd_d32(cudaStream_t s, const Problem& pb, const float* value, const float* loc,
+            const float* attw, float* out) {
+  if (lanes_per_row() == 4) {
+#define CALL(L) launch_fwd_d32<4, L>(s, pb, value, loc, attw, out)
+    MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+  }
+#define CALL(L) launch_fwd_d32<8, L>(s, pb, value, loc, attw, out)
+  MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+}
+template <bool kScatter>
+int bwd_d32(cudaStream_t s, const Problem& pb, const float* go, const float* value,
+            const float* loc, const float* attw, float* gv, float* gl, float* ga) {
+  if (lanes_per_row() == 4) {
+#define CALL(L) launch_bwd_d32<4, L, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
+    MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+  }
+#define CALL(L) launch_bwd_d32<8, L, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
+  MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+}
+
+// ---- templated front ends --------------------------------------------------------------------
+template <typename T>
+int forward_impl(cudaStream_t s, const T* value, const int64_t* shapes, const int64_t* start,
+                 const T* loc, const T* attw, int batch, int spatial_size, int num_heads,
+                 int channels, int num_levels, int num_query, int num_point, T* out,
+                 const msda_opts* opts) {
+  if (!value || !loc || !attw || !out) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  Problem pb;
+  int rc = make_problem(s, shapes, start, batch, spatial_size, num_heads, channels, num_levels,
+                        num_query, num_point, opts, &pb);
+  if (rc != MSDA_OK) return rc;
+  if (batch == 0 || num_query == 0) return MSDA_OK;
+  if constexpr (sizeof(T) == 4) {
+    if (!(pb.flags & MSDA_FLAG_FORCE_GENERIC) && fast_shape(4, channels, num_levels, num_point) &&
+        fits_int32(pb.d) && aligned(value, 32) && aligned(loc, 16) && aligned(attw, 8) &&
+        aligned(out, 16))
+      return fwd_d32(s, pb, value, loc, attw, out);
+  }
+  msda::msda_fwd_generic_kernel<T, T><<<generic_grid(pb.d), 256, 0, s>>>(value, loc, attw, out, pb.lv, pb.d);
+  return after_launch("msda_fwd_generic_kernel");
+}
+
+template <typename T>
+int backward_impl(cudaStream_t s, const T* grad_out, const T* value, const int64_t* shapes,
+                  const int64_t* start, const T* loc, const T* attw, int batch, int spatial_size,
+                  int num_heads, int channels, int num_levels, int num_query, int num_point,
+                  T* gv, T* gl, T* ga, const msda_opts* opts) {
+  if (!grad_out || !value || !loc || !attw || !gv || !gl || !ga)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  Problem pb;
+  int rc = make_problem(s, shapes, start, batch, spatial_size, num_heads, channels, num_levels,
+                        num_query, num_point, opts, &pb);
+  if (rc != MSDA_OK) return rc;
+  if (batch == 0) return MSDA_OK;
+  const bool det = (pb.flags & MSDA_FLAG_DETERMINISTIC) != 0;
+  if (det && sizeof(T) != 4)
+    return fail(MSDA_ERR_UNSUPPORTED, "deterministic mode is implemented for fp32 / bf16 only");
+  const size_t value_bytes = (size_t)batch * spatial_size * num_heads * channels * sizeof(T);
+  // deterministic mode writes every grad_value row itself
+  if (!(pb.flags & MSDA_FLAG_GRAD_VALUE_PREZEROED) && !(det && num_query > 0)) {
+    rc = check_cuda(cudaMemsetAsync(gv, 0, value_bytes, s), "zero-fill of grad_value");
+    if (rc != MSDA_OK) return rc;
+  }
+  if (num_query == 0) return MSDA_OK;
+  bool fast = false;
+  if constexpr (sizeof(T) == 4) {
+    fast = !(pb.flags & MSDA_FLAG_FORCE_GENERIC) && fast_shape(4, channels, num_levels, num_point) &&
+           fits_int32(pb.d) && aligned(value, 32) && aligned(gv, 32) && aligned(loc, 16) &&
+           aligned(attw, 8) && aligned(grad_out, 16) && aligned(gl, 16) && aligned(ga, 8);
+    if (fast) {
+      rc = det ? bwd_d32<false>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
+               : bwd_d32<true>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
+      if (rc != MSDA_OK || !det) return rc;
+    }
+    if (det) {
+      if (!fast) {
+        msda::msda_bwd_generic_kernel<T, T, false><<<generic_grid(pb.d), 256, 0, s>>>(
+            grad_out, value, loc, attw, gv, gl, ga, pb.lv, pb.d);
+        if ((rc = after_launch("msda_bwd_generic_kernel<noscatter>"))) return rc;
+      }
+      return msda::deterministic_grad_value<float>(s, pb.d, pb.lv, (const float*)grad_out, (const float*)loc,
+                                                   (const float*)attw, (float*)gv,
+                                                   opts ? opts->workspace : nullptr,
+                                                   opts ? opts->workspace_bytes : 0);
+    }
+  }
+  msda::msda_bwd_generic_kernel<T, T, true><<<generic_grid(pb.d), 256, 0, s>>>(grad_out, value, loc, attw, gv,
+                                                                            gl, ga, pb.lv, pb.d);
+  return after_launch("msda_bwd_generic_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda_forward_f32(msda_stream_t stream, const float* value, const int64_t* spatial_shapes,
+                     const int64_t* level_start_index, const float* sampling_loc,
+                     const float* attn_weight, int batch, int spatial_size, int num_heads,
+                     int channels, int num_levels, int num_query, int num_point, float* out,
+                     const msda_opts* opts) {
+  return forward_impl<float>((cudaStream_t)stream, value, spatial_shapes, level_start_index,
+                             sampling_loc, attn_weight, batch, spatial_size, num_heads, channels,
+                             num_levels, num_query, num_point, out, opts);
+}
+
+int msda_forward_f64(msda_stream_t stream, const double* value, const int64_t* spatial_shapes,
+                     const int64_t* level_start_index, const double* sampling_loc,
+                     const double* attn_weight, int batch, int spatial_size, int num_heads,
+                     int channels, int num_levels, int num_query, int num_point, double* out,
+                     const msda_opts* opts) {
+  return forward_impl<double>((cudaStream_t)stream, value, spatial_shapes, level_start_index,
+                              sampling_loc, attn_weight, batch, spatial_size, num_heads, channels,
+                              num_levels, num_query, num_point, out, opts);
+}
+
+int msda_backward_f32(msda_stream_t stream, const float* grad_out, const float* value,
+                      const int64_t* spatial_shapes, const int64_t* level_start_index,
+                      const float* sampling_loc, const float* attn_weight, int batch,
+                      int spatial_size, int num_heads, int channels, int num_levels,
+                      int num_query, int num_point, float* grad_value, float* grad_sampling_loc,
+                      float* grad_attn_weight, const msda_opts* opts) {
+  return backward_impl<float>((cudaStream_t)stream, grad_out, value, spatial_shapes,
+                              level_start_index, sampling_loc, attn_weight, batch, spatial_size,
+                              num_heads, channels, num_levels, num_query, num_point, grad_value,
+                              grad_sampling_loc, grad_attn_weight, opts);
+}
+
+int msda_backward_f64(msda_stream_t stream, const double* grad_out, const double* value,
+                      const int64_t* spatial_shapes, const int64_t* level_start_index,
+                      const double* sampling_loc, const double* attn_weight, int batch,
+                      int spatial_size, int num_heads, int channels, int num_levels,
+                      int num_query, int num_point, double* grad_value, double* grad_sampling_loc,
+                      double* grad_attn_weight, const msda_opts* opts) {
+  return backward_impl<double>((cudaStream_t)stream, grad_out, value, spatial_shapes,
+                               level_start_index, sampling_loc, attn_weight, batch, spatial_size,
+                               num_heads, channels, num_levels, num_query, num_point, grad_value,
+                               grad_sampling_loc, grad_attn_weight, opts);
+}
+
+int msda_forward_bf16(msda_stream_t stream, const uint16_t* value, const int64_t* spatial_shapes,
+                      const int64_t* level_start_index, const float* sampling_loc,
+                      const float* attn_weight, int batch, int spatial_size, int num_heads,
+                      int channels, int num_levels, int num_query, int num_point, uint16_t* out,
+                      const msda_opts* opts) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!value || !sampling_loc || !attn_weight || !out)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  Problem pb;
+  int rc = make_problem(s, spatial_shapes, level_start_index, batch, spatial_size, num_heads,
+                        channels, num_levels, num_query, num_point, opts, &pb);
+  if (rc != MSDA_OK) return rc;
+  if (batch == 0 || num_query == 0) return MSDA_OK;
+  return msda::forward_bf16(s, pb.d, pb.lv, pb.order, pb.order_len, pb.flags, value, sampling_loc,
+                            attn_weight, out);
+}
+
+int msda_backward_bf16(msda_stream_t stream, const uint16_t* grad_out, const uint16_t* value,
+                       const int64_t* spatial_shapes, const int64_t* level_start_index,
+                       const float* sampling_loc, const float* attn_weight, int batch,
+                       int spatial_size, int num_heads, int channels, int num_levels,
+                       int num_query, int num_point, float* grad_value, float* grad_sampling_loc,
+                       float* grad_attn_weight, const msda_opts* opts) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!grad_out || !value || !sampling_loc || !attn_weight || !grad_value || !grad_sampling_loc ||
+      !grad_attn_weight)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  Problem pb;
+  int rc = make_problem(s, spatial_shapes, level_start_index, batch, spatial_size, num_heads,
+                        channels, num_levels, num_query, num_point, opts, &pb);
+  if (rc != MSDA_OK) return rc;
+  if (batch == 0) return MSDA_OK;
+  if (!(pb.flags & MSDA_FLAG_GRAD_VALUE_PREZEROED)) {
+    rc = check_cuda(cudaMemsetAsync(grad_value, 0,
+                                    (size_t)batch * spatial_size * num_heads * channels * sizeof(float), s),
+                    "zero-fill of grad_value");
+    if (rc != MSDA_OK) return rc;
+  }
+  if (num_query == 0) return MSDA_OK;
+  return msda::backward_bf16(s, pb.d, pb.lv, pb.order, pb.order_len, pb.flags, grad_out, value,
+                             sampling_loc, attn_weight, grad_value, grad_sampling_loc,
+                             grad_attn_weight, opts ? opts->workspace : nullptr,
+                             opts ? opts->workspace_bytes : 0);
+}
+
+int msda_debug_corners_f32(msda_stream_t stream, const int64_t* spatial_shapes,
+                           const int64_t* level_start_index, const float* sampling_loc, int batch,
+                           int num_heads, int num_levels, int num_query, int num_point,
+                           int32_t* corners, const msda_opts* opts) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!sampling_loc || !corners) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  if (batch < 0 || num_heads < 1 || num_query < 0 || num_point < 1)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "bad dimensions");
+  MsdaLevels lv;
+  int rc = resolve_levels(s, spatial_shapes, level_start_index, num_levels, INT32_MAX, opts, &lv);
+  if (rc != MSDA_OK) return rc;
+  const long long n = (long long)batch * num_query * num_heads * num_levels * num_point;
+  if (n == 0) return MSDA_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  msda::msda_corners_kernel<<<(int)blocks, 256, 0, s>>>(sampling_loc, corners, lv, n, num_levels, num_point);
+  return after_launch("msda_corners_kernel");
+}
+
+size_t msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels,
+                                     int num_levels, int num_query, int num_point) {
+  return msda::deterministic_workspace_bytes(batch, spatial_size, num_heads, channels, num_levels,
+                                             num_query, num_point);
+}
+
+int msda_has_fast_path(int dtype_bytes, int channels, int num_levels, int num_point) {
+  return fast_shape(dtype_bytes, channels, num_levels, num_point) ? 1 : 0;
+}
+
+int msda_abi_version(void) { return MSDA_ABI_VERSION; }
+
+const char* msda_build_info(void) { return "msda_b200 abi " "1" " sm_100a " __DATE__ " " __TIME__; }
+
+const char* msda_last_error(void) { return g_err; }
+
+uint64_t msda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+// msda_common.cuh — shared device helpers for the MSDeformAttn sm_100a kernels.
+//
+// The sample geometry below is THE index contract of the op: it restates, in fp32
+// round-to-nearest with no FMA contraction, what the reference computes at
+// models/richsem/ops/src/cuda/ms_deform_im2col_cuda.cuh:285-288 (pixel coordinates and
+// range test) and :38-78 (floor, fractions, per-corner bounds).  Every kernel in this
+// library (forward, backward, deterministic backward, debug probe) gets its corner
+// indices from msda_sample_geom() and nowhere else.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/msda_b200.h"
+
+// Per-level table; passed by value as a __grid_constant__ kernel parameter, so it lives
+// in the constant bank (c[0x0][..]) and costs no load instructions when the level index
+// is known at compile time.
+struct MsdaLevels {
+  int H[MSDA_MAX_LEVELS];
+  int W[MSDA_MAX_LEVELS];
+  int start[MSDA_MAX_LEVELS];
+};
+
+struct MsdaDims {
+  int batch, spatial_size, num_heads, channels, num_levels, num_query, num_point;
+};
+
+// ---- pixel coordinate: loc * size - 0.5, two separately rounded operations -------------
+// (the reference multiplies in scalar_t and subtracts a double literal, which for float is
+// exactly a rounded multiply followed by a rounded subtract; cuh:285-286)
+__device__ __forceinline__ float msda_pix(float loc, int size) {
+  return __fsub_rn(__fmul_rn(loc, (float)size), 0.5f);
+}
+__device__ __forceinline__ double msda_pix(double loc, int size) {
+  return __dsub_rn(__dmul_rn(loc, (double)size), 0.5);
+}
+
+// Geometry of one sampling point.
+//   tok[k]  token index (into the spatial_size axis) of corner k in the order
+//           (h0,w0) (h0,w1) (h1,w0) (h1,w1); -1 when the corner contributes nothing.
+//   lh, lw  fractional parts (0 when the whole sample is skipped).
+// Returns true when the sample passes the range test of cuh:288.
+template <typename T>
+__device__ __forceinline__ bool msda_sample_geom(T x, T y, int H, int W, int start, int (&tok)[4],
+                                                 T& lh, T& lw) {
+  const T w_im = msda_pix(x, W);
+  const T h_im = msda_pix(y, H);
+  tok[0] = tok[1] = tok[2] = tok[3] = -1;
+  lh = T(0);
+  lw = T(0);
+  // NaN coordinates fail every comparison and are skipped, as in the reference.
+  if (!(h_im > T(-1) && w_im > T(-1) && h_im < T(H) && w_im < T(W))) return false;
+  const T hf = floor(h_im);
+  const T wf = floor(w_im);
+  const int h0 = (int)hf;
+  const int w0 = (int)wf;
+  lh = h_im - hf;
+  lw = w_im - wf;
+  const bool h0ok = h0 >= 0, w0ok = w0 >= 0;
+  const bool h1ok = h0 + 1 <= H - 1, w1ok = w0 + 1 <= W - 1;
+  const int base = start + h0 * W + w0;
+  if (h0ok && w0ok) tok[0] = base;
+  if (h0ok && w1ok) tok[1] = base + 1;
+  if (h1ok && w0ok) tok[2] = base + W;
+  if (h1ok && w1ok) tok[3] = base + W + 1;
+  return true;
+}
+
+// ---- memory helpers ---------------------------------------------------------------------
+// Streaming operands (sampling_loc, attn_weight, grad_out, outputs) are touched once:
+// keep them out of L1 so the gathered `value` rows own it.
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ld_stream_f2(const float* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream_f2(float* p, float2 v) {
+  asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+// 16-byte fp32 vector reduction: one REDG.E.ADD.F32x4 per lane (sm_90+).
+__device__ __forceinline__ void red_add_f4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// Gathered row fragment: C consecutive fp32 channels held by one lane.
+template <int C>
+struct RowFrag;
+template <>
+struct RowFrag<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <>
+struct RowFrag<8> {
+  float v[8];
+  // 32-byte load: LDG.E.256 on sm_100a
+  __device__ __forceinline__ void load(const float* p) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]),
+          "=f"(v[7])
+        : "l"(p));
+  }
+};
+template <int C>
+__device__ __forceinline__ void row_load_or_zero(RowFrag<C>& r, const float* base, int off) {
+  if (off >= 0) {
+    r.load(base + off);
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) r.v[c] = 0.f;
+  }
+}
