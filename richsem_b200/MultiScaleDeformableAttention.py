@@ -101,6 +101,8 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     sfx = _suffix(value, sampling_loc, attn_weight)
     meta = _capi.level_meta(spatial_shapes, level_start_index)
     out = torch.empty((n, lq, m * d), dtype=value.dtype, device=value.device)
+    if out.numel() == 0:
+        return out
     opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=_flags)
     with torch.cuda.device(value.device):
         rc = getattr(_capi.lib, "msda_forward_" + sfx)(
@@ -132,6 +134,8 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     grad_value = torch.empty(value.shape, dtype=aux, device=value.device)  # zero-filled by the library
     grad_loc = torch.empty_like(sampling_loc)
     grad_attw = torch.empty_like(attn_weight)
+    if grad_loc.numel() == 0:  # no queries (or empty batch): nothing is sampled
+        return [grad_value.zero_(), grad_loc, grad_attw]
     flags, ws = _flags, None
     if is_deterministic() and value.dtype != torch.float64:
         flags |= _capi.FLAG_DETERMINISTIC

@@ -13,7 +13,8 @@ from pathlib import Path
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmsda_b200.so"
+# MSDA_B200_LIB selects another build of the same library (kernel-tuning experiments only)
+_LIB_PATH = Path(os.environ.get("MSDA_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libmsda_b200.so")
 
 MSDA_OK = 0
 MSDA_ABI_VERSION = 1

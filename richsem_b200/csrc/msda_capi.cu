@@ -110,16 +110,6 @@ int make_problem(cudaStream_t stream, const int64_t* shapes, const int64_t* star
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-// lanes per value row in the tuned kernels: 8 -> LDG.128, 4 -> LDG.256
-int lanes_per_row() {
-  static const int g = [] {
-    const char* e = getenv("MSDA_B200_LANES_PER_ROW");
-    const int v = e ? atoi(e) : 0;
-    return (v == 4 || v == 8) ? v : 8;
-  }();
-  return g;
-}
-
 bool fast_shape(int dtype_bytes, int channels, int num_levels, int num_point) {
   return (dtype_bytes == 4 || dtype_bytes == 2) && channels == 32 && num_point == 4 &&
          num_levels >= 1 && num_levels <= 6;
@@ -137,24 +127,24 @@ int generic_grid(const MsdaDims& d) {
 }
 
 // ---- tuned fp32 dispatch -------------------------------------------------------------------
-template <int G, int kL>
+template <int kL, int kM>
 int launch_fwd_d32(cudaStream_t s, const Problem& pb, const float* value, const float* loc,
                    const float* attw, float* out) {
-  using Cfg = msda::D32Cfg<G, kL * 4>;
+  using Cfg = msda::D32Cfg<kL * 4>;
   const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
-  msda::msda_fwd_d32_kernel<G, kL, 4><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
+  msda::msda_fwd_d32_kernel<kL, 4, kM><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
       value, loc, attw, out, pb.order, pb.order_len, pb.lv, pb.d.spatial_size, pb.d.num_heads,
       pb.d.num_query);
   return after_launch("msda_fwd_d32_kernel");
 }
-template <int G, int kL, bool kScatter>
+template <int kL, int kM, bool kScatter>
 int launch_bwd_d32(cudaStream_t s, const Problem& pb, const float* grad_out, const float* value,
                    const float* loc, const float* attw, float* gv, float* gl, float* ga) {
-  using Cfg = msda::D32Cfg<G, kL * 4>;
+  using Cfg = msda::D32Cfg<kL * 4>;
   const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
-  msda::msda_bwd_d32_kernel<G, kL, 4, kScatter><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
+  msda::msda_bwd_d32_kernel<kL, 4, kM, kScatter><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
       grad_out, value, loc, attw, gv, gl, ga, pb.order, pb.order_len, pb.lv, pb.d.spatial_size,
       pb.d.num_heads, pb.d.num_query);
   return after_launch("msda_bwd_d32_kernel");
@@ -173,24 +163,21 @@ int launch_bwd_d32(cudaStream_t s, const Problem& pb, const float* grad_out, con
 
 int fwd_d32(cudaStream_t s, const Problem& pb, const float* value, const float* loc,
             const float* attw, float* out) {
-  if (lanes_per_row() == 4) {
-#define CALL(L) launch_fwd_d32<4, L>(s, pb, value, loc, attw, out)
-    MSDA_SWITCH_L(pb.d.num_levels, CALL)
-#undef CALL
-  }
-#define CALL(L) launch_fwd_d32<8, L>(s, pb, value, loc, attw, out)
+  // the DINO / RichSem configuration (8 heads, 4 or 5 levels) gets the head count baked in
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_fwd_d32<4, 8>(s, pb, value, loc, attw, out);
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 5) return launch_fwd_d32<5, 8>(s, pb, value, loc, attw, out);
+#define CALL(L) launch_fwd_d32<L, 0>(s, pb, value, loc, attw, out)
   MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL
 }
 template <bool kScatter>
 int bwd_d32(cudaStream_t s, const Problem& pb, const float* go, const float* value,
             const float* loc, const float* attw, float* gv, float* gl, float* ga) {
-  if (lanes_per_row() == 4) {
-#define CALL(L) launch_bwd_d32<4, L, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
-    MSDA_SWITCH_L(pb.d.num_levels, CALL)
-#undef CALL
-  }
-#define CALL(L) launch_bwd_d32<8, L, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 4)
+    return launch_bwd_d32<4, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 5)
+    return launch_bwd_d32<5, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
+#define CALL(L) launch_bwd_d32<L, 0, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
   MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL
 }
@@ -209,8 +196,7 @@ int forward_impl(cudaStream_t s, const T* value, const int64_t* shapes, const in
   if (batch == 0 || num_query == 0) return MSDA_OK;
   if constexpr (sizeof(T) == 4) {
     if (!(pb.flags & MSDA_FLAG_FORCE_GENERIC) && fast_shape(4, channels, num_levels, num_point) &&
-        fits_int32(pb.d) && aligned(value, 32) && aligned(loc, 16) && aligned(attw, 8) &&
-        aligned(out, 16))
+        fits_int32(pb.d) && aligned(value, 16) && aligned(loc, 8) && aligned(out, 16))
       return fwd_d32(s, pb, value, loc, attw, out);
   }
   msda::msda_fwd_generic_kernel<T, T><<<generic_grid(pb.d), 256, 0, s>>>(value, loc, attw, out, pb.lv, pb.d);
@@ -242,8 +228,8 @@ int backward_impl(cudaStream_t s, const T* grad_out, const T* value, const int64
   bool fast = false;
   if constexpr (sizeof(T) == 4) {
     fast = !(pb.flags & MSDA_FLAG_FORCE_GENERIC) && fast_shape(4, channels, num_levels, num_point) &&
-           fits_int32(pb.d) && aligned(value, 32) && aligned(gv, 32) && aligned(loc, 16) &&
-           aligned(attw, 8) && aligned(grad_out, 16) && aligned(gl, 16) && aligned(ga, 8);
+           fits_int32(pb.d) && aligned(value, 16) && aligned(gv, 16) && aligned(loc, 8) &&
+           aligned(grad_out, 16) && aligned(gl, 8);
     if (fast) {
       rc = det ? bwd_d32<false>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
                : bwd_d32<true>(s, pb, grad_out, value, loc, attw, gv, gl, ga);

@@ -82,6 +82,14 @@ __device__ __forceinline__ float2 ld_stream_f2(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
   return r;
 }
+__device__ __forceinline__ float ld_stream_f1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f1(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w)
@@ -96,34 +104,3 @@ __device__ __forceinline__ void red_add_f4(float* p, float a, float b, float c, 
                : "memory");
 }
 
-// Gathered row fragment: C consecutive fp32 channels held by one lane.
-template <int C>
-struct RowFrag;
-template <>
-struct RowFrag<4> {
-  float v[4];
-  __device__ __forceinline__ void load(const float* p) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-  }
-};
-template <>
-struct RowFrag<8> {
-  float v[8];
-  // 32-byte load: LDG.E.256 on sm_100a
-  __device__ __forceinline__ void load(const float* p) {
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]),
-          "=f"(v[7])
-        : "l"(p));
-  }
-};
-template <int C>
-__device__ __forceinline__ void row_load_or_zero(RowFrag<C>& r, const float* base, int off) {
-  if (off >= 0) {
-    r.load(base + off);
-  } else {
-#pragma unroll
-    for (int c = 0; c < C; ++c) r.v[c] = 0.f;
-  }
-}
