@@ -45,6 +45,8 @@ WORKLOADS = {
     "decoder6_f32": ((800, 1333), 6, 2, "Dn", 1100, "f32"),
     "encoder1_hr1333": ((1333, 1333), 1, 2, "E", None, "f32"),
     "encoder1_hr2000": ((1600, 2000), 1, 2, "E", None, "f32"),
+    # config 4: whole encoder-layer train step (MSDeformAttn + Linear projections + FFN), DDP all-reduce
+    "encoder_layer_ddp": ((800, 1333), 1, 2, "layer", None, "f32"),
 }
 
 
@@ -171,6 +173,30 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------
+# multi-rank helpers (batch sharding: no collective on the data path, ranks meet only here)
+# --------------------------------------------------------------------------------------------
+def max_over_ranks(ms, world, device):
+    """Device time of the slowest rank (the contract's max-over-ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    if world <= 1:
+        return float(ms)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def rank_seed(base, rank, layer):
+    """Every rank / layer gets its own synthetic shard (weak scaling: per-GPU work is fixed)."""
+    return base + 100 * rank + layer
+
+
+def aggregate_qps(queries_per_rank_step, world, ms_per_step):
+    return world * queries_per_rank_step / (ms_per_step * 1e-3)
+
+
+# --------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -190,9 +216,11 @@ def run_b200(args):
     from richsem_b200 import _capi, synthetic as syn
 
     hw, layers, bs, kind, lq, vdt = WORKLOADS[args.workload]
+    if kind == "layer":
+        return run_encoder_layer_ddp(args, torch, dist, rank, world, dev)
     shapes = syn.level_shapes(*hw)
     tdt = torch.bfloat16 if vdt == "bf16" else torch.float32
-    sets = [syn.make_inputs(kind, bs, shapes, dev, seed=1234 + 100 * rank + i, lq=lq, dtype=tdt) for i in range(layers)]
+    sets = [syn.make_inputs(kind, bs, shapes, dev, seed=rank_seed(1234, rank, i), lq=lq, dtype=tdt) for i in range(layers)]
     S, Lq = sets[0]["S"], sets[0]["Lq"]
     shp, st = sets[0]["shapes"], sets[0]["starts"]
     queries_per_step = layers * bs * Lq
@@ -242,13 +270,8 @@ def run_b200(args):
     sync_all()
     launches = _capi.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    ms = start.elapsed_time(stop)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    ms_per_step = ms_max / args.steps
-    value = world * queries_per_step / (ms_per_step * 1e-3)
+    ms_per_step = max_over_ranks(start.elapsed_time(stop), world, dev) / args.steps
+    value = aggregate_qps(queries_per_step, world, ms_per_step)
 
     fwd_ms = statistics.mean(tm["f0"][i].elapsed_time(tm["f1"][i]) for tm in timings for i in range(layers))
     bwd_ms = statistics.mean(tm["b0"][i].elapsed_time(tm["b1"][i]) for tm in timings for i in range(layers))
@@ -301,6 +324,72 @@ def run_b200(args):
         "lib": _capi.build_info(),
     }
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_encoder_layer_ddp(args, torch, dist, rank, world, dev):
+    """BASELINE config 4: per rank one reference-equivalent deformable encoder layer (d_ffn 2048, relu,
+    dropout 0) on its own bs=2 shard; loss = out.square().mean(); forward + backward with DDP's bucketed
+    NCCL all-reduce of the 1,282,176 fp32 parameters; no optimizer step."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    from richsem_b200 import _capi, synthetic as syn
+    from richsem_b200.encoder_layer import DeformableEncoderLayer, encoder_reference_points
+
+    hw, _, bs, _, _, _ = WORKLOADS[args.workload]
+    shapes = syn.level_shapes(*hw)
+    shp, st, S = syn.level_tensors(shapes, dev)
+    torch.manual_seed(1234)
+    layer = DeformableEncoderLayer().to(dev)
+    with torch.no_grad():  # leave the degenerate init so that every gradient path does real work
+        layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+        layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+    n_params = sum(p.numel() for p in layer.parameters())
+    model = DDP(layer, device_ids=[dev.index]) if world > 1 else layer
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    src = torch.randn(bs, S, 256, generator=gen, device=dev)
+    pos = torch.randn(bs, S, 256, generator=gen, device=dev)
+    ref = encoder_reference_points(shapes, bs, dev)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        out = model(src, pos, ref, shp, st, None)
+        out.square().mean().backward()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    l0 = _capi.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = _capi.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": world * bs * S / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "image": f"{hw[0]}x{hw[1]}", "S": S, "batch_per_gpu": bs,
+                       "params": n_params, "parallelism": f"DDP x{world} (NCCL all-reduce of {n_params * 4 / 1e6:.2f} MB)",
+                       "step": "encoder layer fwd + bwd (MSDeformAttn on libmsda_b200, Linears/LayerNorm in PyTorch), "
+                               "no optimizer"},
+            "gpu_launches": int(launches), "clocks": clocks, "lib": _capi.build_info()}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -24,6 +24,8 @@ import torch
 from . import _capi
 
 _SUFFIX = {torch.float32: "f32", torch.float64: "f64", torch.bfloat16: "bf16"}
+_FWD = {k: getattr(_capi.lib, "msda_forward_" + k) for k in ("f32", "f64", "bf16")}
+_BWD = {k: getattr(_capi.lib, "msda_backward_" + k) for k in ("f32", "f64", "bf16")}
 _state = {"deterministic": os.environ.get("MSDA_B200_DETERMINISTIC", "0") not in ("", "0")}
 _workspaces: dict = {}
 
@@ -85,12 +87,34 @@ def _suffix(value, sampling_loc, attn_weight):
     return sfx
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def _stream(device):
+    if _raw_stream is not None:
+        return _raw_stream(device.index)
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def _dev_ptr(t):
     return t.data_ptr() if t.is_cuda else None
+
+
+class _on_device:
+    """Makes `device` current for the launch; free when it already is (the common case)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
 
 
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step,
@@ -104,9 +128,9 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     if out.numel() == 0:
         return out
     opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=_flags)
-    with torch.cuda.device(value.device):
-        rc = getattr(_capi.lib, "msda_forward_" + sfx)(
-            _stream(), value.data_ptr(), _dev_ptr(spatial_shapes), _dev_ptr(level_start_index),
+    with _on_device(value.device):
+        rc = _FWD[sfx](
+            _stream(value.device), value.data_ptr(), _dev_ptr(spatial_shapes), _dev_ptr(level_start_index),
             sampling_loc.data_ptr(), attn_weight.data_ptr(), n, s, m, d, nl, lq, npt, out.data_ptr(), opts)
     _capi.check(rc, "msda_forward_" + sfx)
     return out
@@ -142,9 +166,9 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     if flags & _capi.FLAG_DETERMINISTIC:
         ws = _workspace(_capi.lib.msda_backward_workspace_bytes(n, s, m, d, nl, lq, npt), value.device)
     opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=flags, workspace=ws)
-    with torch.cuda.device(value.device):
-        rc = getattr(_capi.lib, "msda_backward_" + sfx)(
-            _stream(), grad_output.data_ptr(), value.data_ptr(), _dev_ptr(spatial_shapes),
+    with _on_device(value.device):
+        rc = _BWD[sfx](
+            _stream(value.device), grad_output.data_ptr(), value.data_ptr(), _dev_ptr(spatial_shapes),
             _dev_ptr(level_start_index), sampling_loc.data_ptr(), attn_weight.data_ptr(), n, s, m, d, nl, lq, npt,
             grad_value.data_ptr(), grad_loc.data_ptr(), grad_attw.data_ptr(), opts)
     _capi.check(rc, "msda_backward_" + sfx)
@@ -159,8 +183,8 @@ def debug_corners(spatial_shapes, level_start_index, sampling_loc):
     n, lq, m, nl, npt, _ = sampling_loc.shape
     meta = _capi.level_meta(spatial_shapes, level_start_index)
     out = torch.empty((n, lq, m, nl, npt, 4), dtype=torch.int32, device=sampling_loc.device)
-    with torch.cuda.device(sampling_loc.device):
-        rc = _capi.lib.msda_debug_corners_f32(_stream(), _dev_ptr(spatial_shapes), _dev_ptr(level_start_index),
+    with _on_device(sampling_loc.device):
+        rc = _capi.lib.msda_debug_corners_f32(_stream(sampling_loc.device), _dev_ptr(spatial_shapes), _dev_ptr(level_start_index),
                                               sampling_loc.data_ptr(), n, m, nl, lq, npt, out.data_ptr(),
                                               _capi.make_opts(meta))
     _capi.check(rc, "msda_debug_corners_f32")

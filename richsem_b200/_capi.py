@@ -21,6 +21,7 @@ MSDA_ABI_VERSION = 1
 FLAG_DETERMINISTIC = 0x1
 FLAG_GRAD_VALUE_PREZEROED = 0x2
 FLAG_FORCE_GENERIC = 0x4
+FLAG_NO_SPLIT = 0x8
 MAX_LEVELS = 16
 
 _vp, _i, _i64p = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)
@@ -187,7 +188,26 @@ def query_order(meta: LevelMeta, num_query: int, device) -> "torch.Tensor | None
     return t
 
 
+_opts_cache: dict = {}
+
+
 def make_opts(meta: LevelMeta, order=None, flags=0, workspace=None) -> MsdaOpts:
+    """msda_opts for a launch.  Structs are immutable once built, so they are cached per
+    (level table, order buffer, flags, workspace) to keep the per-call host cost down."""
+    key = (id(meta), order.data_ptr() if order is not None else 0, flags,
+           workspace.data_ptr() if workspace is not None else 0,
+           workspace.numel() if workspace is not None else 0)
+    hit = _opts_cache.get(key)
+    if hit is not None and hit[1] is meta:
+        return hit[0]
+    o = _build_opts(meta, order, flags, workspace)
+    if len(_opts_cache) > 512:
+        _opts_cache.clear()
+    _opts_cache[key] = (o, meta, order, workspace)  # keep the referenced buffers alive
+    return o
+
+
+def _build_opts(meta, order, flags, workspace) -> MsdaOpts:
     o = MsdaOpts()
     o.struct_size = ctypes.sizeof(MsdaOpts)
     o.flags = flags

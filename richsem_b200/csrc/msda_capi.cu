@@ -7,7 +7,6 @@
 #include <cstring>
 
 #include "msda_host.h"
-#include "msda_bf16.cuh"
 #include "msda_d32.cuh"
 #include "msda_det.cuh"
 #include "msda_generic.cuh"
@@ -126,28 +125,54 @@ int generic_grid(const MsdaDims& d) {
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
-// ---- tuned fp32 dispatch -------------------------------------------------------------------
-template <int kL, int kM>
-int launch_fwd_d32(cudaStream_t s, const Problem& pb, const float* value, const float* loc,
-                   const float* attw, float* out) {
-  using Cfg = msda::D32Cfg<kL * 4>;
+// ---- tuned D=32 dispatch (fp32 and bf16 value) -----------------------------------------------
+template <typename VT, int kL, int kM>
+int launch_fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const float* loc,
+                   const float* attw, VT* out) {
+  using Cfg = msda::D32Cfg<VT, kL * 4>;
   const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
-  msda::msda_fwd_d32_kernel<kL, 4, kM><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
+  msda::msda_fwd_d32_kernel<VT, kL, 4, kM><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
       value, loc, attw, out, pb.order, pb.order_len, pb.lv, pb.d.spatial_size, pb.d.num_heads,
       pb.d.num_query);
   return after_launch("msda_fwd_d32_kernel");
 }
-template <int kL, int kM, bool kScatter>
-int launch_bwd_d32(cudaStream_t s, const Problem& pb, const float* grad_out, const float* value,
+template <typename VT, int kL, int kM, bool kScatter>
+int launch_bwd_d32(cudaStream_t s, const Problem& pb, const VT* grad_out, const VT* value,
                    const float* loc, const float* attw, float* gv, float* gl, float* ga) {
-  using Cfg = msda::D32Cfg<kL * 4>;
+  using Cfg = msda::D32Cfg<VT, kL * 4>;
   const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
-  msda::msda_bwd_d32_kernel<kL, 4, kM, kScatter><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
+  msda::msda_bwd_d32_kernel<VT, kL, 4, kM, kScatter><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
       grad_out, value, loc, attw, gv, gl, ga, pb.order, pb.order_len, pb.lv, pb.d.spatial_size,
       pb.d.num_heads, pb.d.num_query);
   return after_launch("msda_bwd_d32_kernel");
+}
+
+template <typename VT, int kL, int kM>
+int launch_fwd_split(cudaStream_t s, const Problem& pb, const VT* value, const float* loc,
+                     const float* attw, VT* out) {
+  constexpr int QPB = msda::kSplitThreads / 32;
+  dim3 grid(((pb.d.num_query + QPB - 1) / QPB) * pb.d.num_heads, pb.d.batch);
+  msda::msda_fwd_d32_split_kernel<VT, kL, 4, kM><<<grid, msda::kSplitThreads, 0, s>>>(
+      value, loc, attw, out, pb.lv, pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
+  return after_launch("msda_fwd_d32_split_kernel");
+}
+template <typename VT, int kL, int kM, bool kScatter>
+int launch_bwd_split(cudaStream_t s, const Problem& pb, const VT* grad_out, const VT* value,
+                     const float* loc, const float* attw, float* gv, float* gl, float* ga) {
+  constexpr int QPB = msda::kSplitThreads / 32;
+  dim3 grid(((pb.d.num_query + QPB - 1) / QPB) * pb.d.num_heads, pb.d.batch);
+  msda::msda_bwd_d32_split_kernel<VT, kL, 4, kM, kScatter><<<grid, msda::kSplitThreads, 0, s>>>(
+      grad_out, value, loc, attw, gv, gl, ga, pb.lv, pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
+  return after_launch("msda_bwd_d32_split_kernel");
+}
+
+// Few (query, head) pairs (decoder cross-attention): one warp per pair instead of one lane group.
+inline bool use_split(const Problem& pb) {
+  return !(pb.flags & MSDA_FLAG_NO_SPLIT) &&
+         (long long)pb.d.batch * pb.d.num_query * pb.d.num_heads <= 65536 && pb.d.num_levels >= 2 &&
+         pb.d.num_levels <= 6;
 }
 
 #define MSDA_SWITCH_L(L_, CALL)                                                              \
@@ -161,32 +186,47 @@ int launch_bwd_d32(cudaStream_t s, const Problem& pb, const float* grad_out, con
     default: return fail(MSDA_ERR_UNSUPPORTED, "no tuned kernel for num_levels=%d", L_);      \
   }
 
-int fwd_d32(cudaStream_t s, const Problem& pb, const float* value, const float* loc,
-            const float* attw, float* out) {
+template <typename VT>
+int fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const float* loc, const float* attw,
+            VT* out) {
+  if (use_split(pb)) {
+    if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_fwd_split<VT, 4, 8>(s, pb, value, loc, attw, out);
+#define CALL(L) launch_fwd_split<VT, L, 0>(s, pb, value, loc, attw, out)
+    MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+  }
   // the DINO / RichSem configuration (8 heads, 4 or 5 levels) gets the head count baked in
-  if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_fwd_d32<4, 8>(s, pb, value, loc, attw, out);
-  if (pb.d.num_heads == 8 && pb.d.num_levels == 5) return launch_fwd_d32<5, 8>(s, pb, value, loc, attw, out);
-#define CALL(L) launch_fwd_d32<L, 0>(s, pb, value, loc, attw, out)
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_fwd_d32<VT, 4, 8>(s, pb, value, loc, attw, out);
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 5) return launch_fwd_d32<VT, 5, 8>(s, pb, value, loc, attw, out);
+#define CALL(L) launch_fwd_d32<VT, L, 0>(s, pb, value, loc, attw, out)
   MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL
 }
-template <bool kScatter>
-int bwd_d32(cudaStream_t s, const Problem& pb, const float* go, const float* value,
-            const float* loc, const float* attw, float* gv, float* gl, float* ga) {
+template <typename VT, bool kScatter>
+int bwd_d32(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
+            const float* attw, float* gv, float* gl, float* ga) {
+  if (use_split(pb)) {
+    if (pb.d.num_heads == 8 && pb.d.num_levels == 4)
+      return launch_bwd_split<VT, 4, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
+#define CALL(L) launch_bwd_split<VT, L, 0, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
+    MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+  }
   if (pb.d.num_heads == 8 && pb.d.num_levels == 4)
-    return launch_bwd_d32<4, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
+    return launch_bwd_d32<VT, 4, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
   if (pb.d.num_heads == 8 && pb.d.num_levels == 5)
-    return launch_bwd_d32<5, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
-#define CALL(L) launch_bwd_d32<L, 0, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
+    return launch_bwd_d32<VT, 5, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
+#define CALL(L) launch_bwd_d32<VT, L, 0, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
   MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL
 }
 
 // ---- templated front ends --------------------------------------------------------------------
-template <typename T>
-int forward_impl(cudaStream_t s, const T* value, const int64_t* shapes, const int64_t* start,
-                 const T* loc, const T* attw, int batch, int spatial_size, int num_heads,
-                 int channels, int num_levels, int num_query, int num_point, T* out,
+// TV: storage type of value / out / grad_out;  TA: type of locations, weights and all gradients.
+template <typename TV, typename TA>
+int forward_impl(cudaStream_t s, const TV* value, const int64_t* shapes, const int64_t* start,
+                 const TA* loc, const TA* attw, int batch, int spatial_size, int num_heads,
+                 int channels, int num_levels, int num_query, int num_point, TV* out,
                  const msda_opts* opts) {
   if (!value || !loc || !attw || !out) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
   Problem pb;
@@ -194,20 +234,20 @@ int forward_impl(cudaStream_t s, const T* value, const int64_t* shapes, const in
                         num_query, num_point, opts, &pb);
   if (rc != MSDA_OK) return rc;
   if (batch == 0 || num_query == 0) return MSDA_OK;
-  if constexpr (sizeof(T) == 4) {
-    if (!(pb.flags & MSDA_FLAG_FORCE_GENERIC) && fast_shape(4, channels, num_levels, num_point) &&
+  if constexpr (sizeof(TA) == 4) {
+    if (!(pb.flags & MSDA_FLAG_FORCE_GENERIC) && fast_shape(sizeof(TV), channels, num_levels, num_point) &&
         fits_int32(pb.d) && aligned(value, 16) && aligned(loc, 8) && aligned(out, 16))
-      return fwd_d32(s, pb, value, loc, attw, out);
+      return fwd_d32<TV>(s, pb, value, loc, attw, out);
   }
-  msda::msda_fwd_generic_kernel<T, T><<<generic_grid(pb.d), 256, 0, s>>>(value, loc, attw, out, pb.lv, pb.d);
+  msda::msda_fwd_generic_kernel<TV, TA><<<generic_grid(pb.d), 256, 0, s>>>(value, loc, attw, out, pb.lv, pb.d);
   return after_launch("msda_fwd_generic_kernel");
 }
 
-template <typename T>
-int backward_impl(cudaStream_t s, const T* grad_out, const T* value, const int64_t* shapes,
-                  const int64_t* start, const T* loc, const T* attw, int batch, int spatial_size,
+template <typename TV, typename TA>
+int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int64_t* shapes,
+                  const int64_t* start, const TA* loc, const TA* attw, int batch, int spatial_size,
                   int num_heads, int channels, int num_levels, int num_query, int num_point,
-                  T* gv, T* gl, T* ga, const msda_opts* opts) {
+                  TA* gv, TA* gl, TA* ga, const msda_opts* opts) {
   if (!grad_out || !value || !loc || !attw || !gv || !gl || !ga)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
   Problem pb;
@@ -216,39 +256,38 @@ int backward_impl(cudaStream_t s, const T* grad_out, const T* value, const int64
   if (rc != MSDA_OK) return rc;
   if (batch == 0) return MSDA_OK;
   const bool det = (pb.flags & MSDA_FLAG_DETERMINISTIC) != 0;
-  if (det && sizeof(T) != 4)
+  if (det && sizeof(TA) != 4)
     return fail(MSDA_ERR_UNSUPPORTED, "deterministic mode is implemented for fp32 / bf16 only");
-  const size_t value_bytes = (size_t)batch * spatial_size * num_heads * channels * sizeof(T);
+  const size_t gv_bytes = (size_t)batch * spatial_size * num_heads * channels * sizeof(TA);
   // deterministic mode writes every grad_value row itself
   if (!(pb.flags & MSDA_FLAG_GRAD_VALUE_PREZEROED) && !(det && num_query > 0)) {
-    rc = check_cuda(cudaMemsetAsync(gv, 0, value_bytes, s), "zero-fill of grad_value");
+    rc = check_cuda(cudaMemsetAsync(gv, 0, gv_bytes, s), "zero-fill of grad_value");
     if (rc != MSDA_OK) return rc;
   }
   if (num_query == 0) return MSDA_OK;
-  bool fast = false;
-  if constexpr (sizeof(T) == 4) {
-    fast = !(pb.flags & MSDA_FLAG_FORCE_GENERIC) && fast_shape(4, channels, num_levels, num_point) &&
-           fits_int32(pb.d) && aligned(value, 16) && aligned(gv, 16) && aligned(loc, 8) &&
-           aligned(grad_out, 16) && aligned(gl, 8);
+  if constexpr (sizeof(TA) == 4) {
+    const bool fast = !(pb.flags & MSDA_FLAG_FORCE_GENERIC) &&
+                      fast_shape(sizeof(TV), channels, num_levels, num_point) && fits_int32(pb.d) &&
+                      aligned(value, 16) && aligned(gv, 16) && aligned(loc, 8) && aligned(grad_out, 16) &&
+                      aligned(gl, 8);
     if (fast) {
-      rc = det ? bwd_d32<false>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
-               : bwd_d32<true>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
+      rc = det ? bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
+               : bwd_d32<TV, true>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
       if (rc != MSDA_OK || !det) return rc;
     }
     if (det) {
       if (!fast) {
-        msda::msda_bwd_generic_kernel<T, T, false><<<generic_grid(pb.d), 256, 0, s>>>(
+        msda::msda_bwd_generic_kernel<TV, TA, false><<<generic_grid(pb.d), 256, 0, s>>>(
             grad_out, value, loc, attw, gv, gl, ga, pb.lv, pb.d);
         if ((rc = after_launch("msda_bwd_generic_kernel<noscatter>"))) return rc;
       }
-      return msda::deterministic_grad_value<float>(s, pb.d, pb.lv, (const float*)grad_out, (const float*)loc,
-                                                   (const float*)attw, (float*)gv,
-                                                   opts ? opts->workspace : nullptr,
-                                                   opts ? opts->workspace_bytes : 0);
+      return msda::deterministic_grad_value<TV>(s, pb.d, pb.lv, grad_out, loc, attw, gv,
+                                                opts ? opts->workspace : nullptr,
+                                                opts ? opts->workspace_bytes : 0);
     }
   }
-  msda::msda_bwd_generic_kernel<T, T, true><<<generic_grid(pb.d), 256, 0, s>>>(grad_out, value, loc, attw, gv,
-                                                                            gl, ga, pb.lv, pb.d);
+  msda::msda_bwd_generic_kernel<TV, TA, true><<<generic_grid(pb.d), 256, 0, s>>>(grad_out, value, loc, attw, gv,
+                                                                              gl, ga, pb.lv, pb.d);
   return after_launch("msda_bwd_generic_kernel");
 }
 
@@ -261,7 +300,7 @@ int msda_forward_f32(msda_stream_t stream, const float* value, const int64_t* sp
                      const float* attn_weight, int batch, int spatial_size, int num_heads,
                      int channels, int num_levels, int num_query, int num_point, float* out,
                      const msda_opts* opts) {
-  return forward_impl<float>((cudaStream_t)stream, value, spatial_shapes, level_start_index,
+  return forward_impl<float, float>((cudaStream_t)stream, value, spatial_shapes, level_start_index,
                              sampling_loc, attn_weight, batch, spatial_size, num_heads, channels,
                              num_levels, num_query, num_point, out, opts);
 }
@@ -271,7 +310,7 @@ int msda_forward_f64(msda_stream_t stream, const double* value, const int64_t* s
                      const double* attn_weight, int batch, int spatial_size, int num_heads,
                      int channels, int num_levels, int num_query, int num_point, double* out,
                      const msda_opts* opts) {
-  return forward_impl<double>((cudaStream_t)stream, value, spatial_shapes, level_start_index,
+  return forward_impl<double, double>((cudaStream_t)stream, value, spatial_shapes, level_start_index,
                               sampling_loc, attn_weight, batch, spatial_size, num_heads, channels,
                               num_levels, num_query, num_point, out, opts);
 }
@@ -282,7 +321,7 @@ int msda_backward_f32(msda_stream_t stream, const float* grad_out, const float* 
                       int spatial_size, int num_heads, int channels, int num_levels,
                       int num_query, int num_point, float* grad_value, float* grad_sampling_loc,
                       float* grad_attn_weight, const msda_opts* opts) {
-  return backward_impl<float>((cudaStream_t)stream, grad_out, value, spatial_shapes,
+  return backward_impl<float, float>((cudaStream_t)stream, grad_out, value, spatial_shapes,
                               level_start_index, sampling_loc, attn_weight, batch, spatial_size,
                               num_heads, channels, num_levels, num_query, num_point, grad_value,
                               grad_sampling_loc, grad_attn_weight, opts);
@@ -294,7 +333,7 @@ int msda_backward_f64(msda_stream_t stream, const double* grad_out, const double
                       int spatial_size, int num_heads, int channels, int num_levels,
                       int num_query, int num_point, double* grad_value, double* grad_sampling_loc,
                       double* grad_attn_weight, const msda_opts* opts) {
-  return backward_impl<double>((cudaStream_t)stream, grad_out, value, spatial_shapes,
+  return backward_impl<double, double>((cudaStream_t)stream, grad_out, value, spatial_shapes,
                                level_start_index, sampling_loc, attn_weight, batch, spatial_size,
                                num_heads, channels, num_levels, num_query, num_point, grad_value,
                                grad_sampling_loc, grad_attn_weight, opts);
@@ -305,16 +344,10 @@ int msda_forward_bf16(msda_stream_t stream, const uint16_t* value, const int64_t
                       const float* attn_weight, int batch, int spatial_size, int num_heads,
                       int channels, int num_levels, int num_query, int num_point, uint16_t* out,
                       const msda_opts* opts) {
-  cudaStream_t s = (cudaStream_t)stream;
-  if (!value || !sampling_loc || !attn_weight || !out)
-    return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
-  Problem pb;
-  int rc = make_problem(s, spatial_shapes, level_start_index, batch, spatial_size, num_heads,
-                        channels, num_levels, num_query, num_point, opts, &pb);
-  if (rc != MSDA_OK) return rc;
-  if (batch == 0 || num_query == 0) return MSDA_OK;
-  return msda::forward_bf16(s, pb.d, pb.lv, pb.order, pb.order_len, pb.flags, value, sampling_loc,
-                            attn_weight, out);
+  return forward_impl<__nv_bfloat16, float>(
+      (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(value), spatial_shapes,
+      level_start_index, sampling_loc, attn_weight, batch, spatial_size, num_heads, channels,
+      num_levels, num_query, num_point, reinterpret_cast<__nv_bfloat16*>(out), opts);
 }
 
 int msda_backward_bf16(msda_stream_t stream, const uint16_t* grad_out, const uint16_t* value,
@@ -323,26 +356,11 @@ int msda_backward_bf16(msda_stream_t stream, const uint16_t* grad_out, const uin
                        int spatial_size, int num_heads, int channels, int num_levels,
                        int num_query, int num_point, float* grad_value, float* grad_sampling_loc,
                        float* grad_attn_weight, const msda_opts* opts) {
-  cudaStream_t s = (cudaStream_t)stream;
-  if (!grad_out || !value || !sampling_loc || !attn_weight || !grad_value || !grad_sampling_loc ||
-      !grad_attn_weight)
-    return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
-  Problem pb;
-  int rc = make_problem(s, spatial_shapes, level_start_index, batch, spatial_size, num_heads,
-                        channels, num_levels, num_query, num_point, opts, &pb);
-  if (rc != MSDA_OK) return rc;
-  if (batch == 0) return MSDA_OK;
-  if (!(pb.flags & MSDA_FLAG_GRAD_VALUE_PREZEROED)) {
-    rc = check_cuda(cudaMemsetAsync(grad_value, 0,
-                                    (size_t)batch * spatial_size * num_heads * channels * sizeof(float), s),
-                    "zero-fill of grad_value");
-    if (rc != MSDA_OK) return rc;
-  }
-  if (num_query == 0) return MSDA_OK;
-  return msda::backward_bf16(s, pb.d, pb.lv, pb.order, pb.order_len, pb.flags, grad_out, value,
-                             sampling_loc, attn_weight, grad_value, grad_sampling_loc,
-                             grad_attn_weight, opts ? opts->workspace : nullptr,
-                             opts ? opts->workspace_bytes : 0);
+  return backward_impl<__nv_bfloat16, float>(
+      (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(grad_out),
+      reinterpret_cast<const __nv_bfloat16*>(value), spatial_shapes, level_start_index, sampling_loc,
+      attn_weight, batch, spatial_size, num_heads, channels, num_levels, num_query, num_point,
+      grad_value, grad_sampling_loc, grad_attn_weight, opts);
 }
 
 int msda_debug_corners_f32(msda_stream_t stream, const int64_t* spatial_shapes,

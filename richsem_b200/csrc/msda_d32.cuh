@@ -1,27 +1,30 @@
-// msda_d32.cuh — tuned fp32 kernels for head_dim (channels) == 32.
+// msda_d32.cuh — tuned kernels for head_dim (channels) == 32; fp32 and bf16 value.
 //
 // Work decomposition (both directions)
 //   grid  = (num_heads * tiles, batch); one thread block = ONE head x a tile of kTileQ
 //           queries taken from `order` (patch-tiled for encoder self-attention, natural
 //           order otherwise).  Heads sample in different directions, so a block that sticks
 //           to one head keeps the value rows it gathers resident in L1.
-//   warp  = four "lane groups" of 8 lanes; one lane group = one (query, head) pair.  The 8
-//           lanes cover the 32 channels of a value row with one LDG.128 each, so a gathered
-//           row is always one full 128-byte line = one L1 wavefront.
-//   stage 1 lane j of a group decodes sampling points j, j+8, ...: bit-exact geometry
+//   warp  = 32/G "lane groups"; one lane group = one (query, head) pair.  Each lane covers
+//           its share of the 32 channels of a value row with ONE 16-byte load:
+//             fp32 value: G = 8 lanes x 4 channels  (row = 128 B = one full L1 line)
+//             bf16 value: G = 4 lanes x 8 channels  (row =  64 B)
+//   stage 1 lane j of a group decodes sampling points j, j+G, ...: bit-exact geometry
 //           (msda_sample_geom) and a 16-byte record {row offset | corner mask, lh, lw, a}
 //           per point, published to shared memory (conflict-free STS.128).
 //   stage 2 all lanes of the group walk the L*P records (one broadcast LDS.128 per point),
-//           rebuild the four corner offsets / weights in registers, issue the four
-//           predicated row gathers and blend.
-// The kernels are bound by the L1/shared data pipe (4 gather wavefronts per point are
-// compulsory for fp32 rows), so everything else is organised to spend as few extra
-// wavefronts as possible: 16-byte records, shuffle-light reductions in the backward.
+//           rebuild the corner addresses / weights in registers, issue the four predicated
+//           row gathers and blend (forward) or dot / scatter (backward).
+// What binds them (ncu, profiles/): forward — the L1/shared data pipe (4 gathered rows per
+// point are compulsory) together with instruction issue; backward — the chip-wide fp32
+// reduction rate of L2 (REDG.E.ADD.F32x4, ~6.4 TB/s of payload measured in isolation).
 //
 // Algorithm restated from models/richsem/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299
 // (forward), :87-159 and :301-403 (backward); nothing is shared with that code's thread
 // mapping (one thread per output channel, one-warp blocks, serial reductions).
 #pragma once
+
+#include <cuda_bf16.h>
 
 #include "msda_common.cuh"
 
@@ -36,15 +39,63 @@ namespace msda {
 constexpr int kThreads = MSDA_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTileQ = 64;  // queries per thread block
-constexpr int kG = 8;       // lanes per (query, head)
-constexpr int kC = 4;       // channels per lane
 
-template <int LP>
+// ---- per-value-type traits ----------------------------------------------------------------
+template <typename VT>
+struct RowTraits;
+template <>
+struct RowTraits<float> {
+  static constexpr int G = 8, C = 4;  // lanes per row, channels per lane
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void load_stream(const float* p, float (&v)[4]) {
+    const float4 t = ld_stream_f4(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store_stream(float* p, const float (&v)[4]) {
+    st_stream_f4(p, make_float4(v[0], v[1], v[2], v[3]));
+  }
+};
+template <>
+struct RowTraits<__nv_bfloat16> {
+  static constexpr int G = 4, C = 8;
+  static __device__ __forceinline__ void unpack(const uint4 t, float (&v)[8]) {
+    // bf16 -> fp32 is a 16-bit shift: low half = even channel, high half = odd channel
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xffff0000u);
+    v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    unpack(__ldg(reinterpret_cast<const uint4*>(p)), v);
+  }
+  static __device__ __forceinline__ void load_stream(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 t;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+    unpack(t, v);
+  }
+  static __device__ __forceinline__ void store_stream(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162 h;
+    h = __floats2bfloat162_rn(v[0], v[1]); t.x = *reinterpret_cast<unsigned*>(&h);
+    h = __floats2bfloat162_rn(v[2], v[3]); t.y = *reinterpret_cast<unsigned*>(&h);
+    h = __floats2bfloat162_rn(v[4], v[5]); t.z = *reinterpret_cast<unsigned*>(&h);
+    h = __floats2bfloat162_rn(v[6], v[7]); t.w = *reinterpret_cast<unsigned*>(&h);
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
+  }
+};
+
+template <typename VT, int LP>
 struct D32Cfg {
-  static constexpr int GPW = 32 / kG;                 // (query, head) pairs per warp
+  static constexpr int G = RowTraits<VT>::G;
+  static constexpr int C = RowTraits<VT>::C;
+  static constexpr int GPW = 32 / G;                  // (query, head) pairs per warp
   static constexpr int QPP = kWarps * GPW;            // queries per pass of the block
   static constexpr int PASSES = kTileQ / QPP;
-  static constexpr int KP = (LP + kG - 1) / kG;       // points decoded per lane
+  static constexpr int KP = (LP + G - 1) / G;         // points decoded per lane
   static constexpr int REC_STRIDE = LP + 1;           // float4 units per lane group (+1: bank skew)
   static constexpr int SMEM_BYTES = kWarps * GPW * REC_STRIDE * 16;
   static_assert(kTileQ % QPP == 0, "tile must be a whole number of passes");
@@ -53,15 +104,15 @@ struct D32Cfg {
 // Decodes this lane's points of (query, head) `qm` and publishes their records.
 // record.x = element offset of corner (h0,w0)'s row within the image's value block
 //            (a multiple of 32, possibly "virtual" when h0 or w0 is -1) | 4-bit corner mask
-template <int kL, int kP>
+template <int G, int kL, int kP>
 __device__ __forceinline__ void d32_decode_points(const float* __restrict__ loc,
                                                   const float* __restrict__ attw, const size_t qm,
                                                   const int j, const int m, const int M,
                                                   const MsdaLevels& lv, float4* rec) {
   constexpr int LP = kL * kP;
 #pragma unroll
-  for (int k = 0; k < D32Cfg<LP>::KP; ++k) {
-    const int p = j + kG * k;
+  for (int k = 0; k < (LP + G - 1) / G; ++k) {
+    const int p = j + G * k;
     if (p < LP) {
       const int l = p / kP;
       const float2 xy = ld_stream_f2(loc + (qm * LP + p) * 2);
@@ -85,26 +136,28 @@ __device__ __forceinline__ void d32_decode_points(const float* __restrict__ loc,
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
-template <int kL, int kP, int kM>
+template <typename VT, int kL, int kP, int kM>
 __global__ void __launch_bounds__(kThreads)
-msda_fwd_d32_kernel(const float* __restrict__ value, const float* __restrict__ loc,
-                    const float* __restrict__ attw, float* __restrict__ out,
+msda_fwd_d32_kernel(const VT* __restrict__ value, const float* __restrict__ loc,
+                    const float* __restrict__ attw, VT* __restrict__ out,
                     const int* __restrict__ order, const int order_len,
                     const __grid_constant__ MsdaLevels lv, const int S, const int M_rt, const int Lq) {
   constexpr int LP = kL * kP;
-  using Cfg = D32Cfg<LP>;
+  using Cfg = D32Cfg<VT, LP>;
+  using RT = RowTraits<VT>;
+  constexpr int G = Cfg::G, C = Cfg::C;
   extern __shared__ float4 smem[];
   const int M = kM ? kM : M_rt;  // kM > 0: number of heads known at compile time
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane / kG, j = lane % kG;
+  const int g = lane / G, j = lane % G;
   const int m = blockIdx.x % M;
   const int tile = blockIdx.x / M;
   const int b = blockIdx.y;
   const int M32 = M * 32;
 
   float4* rec = smem + (warp * Cfg::GPW + g) * Cfg::REC_STRIDE;
-  const float* value_b = value + (size_t)b * S * M32 + j * kC;
+  const VT* value_b = value + (size_t)b * S * M32 + j * C;
 
 #pragma unroll 1
   for (int pass = 0; pass < Cfg::PASSES; ++pass) {
@@ -114,11 +167,13 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const float* __restrict__ l
     const bool active = q >= 0;
     const size_t qm = ((size_t)b * Lq + (active ? q : 0)) * M + m;
 
-    if (active) d32_decode_points<kL, kP>(loc, attw, qm, j, m, M, lv, rec);
+    if (active) d32_decode_points<G, kL, kP>(loc, attw, qm, j, m, M, lv, rec);
     __syncwarp();
 
     if (active) {
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      float acc[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = 0.f;
 #pragma unroll
       for (int p = 0; p < LP; ++p) {
         const int l = p / kP;
@@ -127,85 +182,88 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const float* __restrict__ l
         const float lh = r.y, lw = r.z, a = r.w;
         const float a_hh = a * (1.f - lh), a_lh = a * lh, hw = 1.f - lw;
         // one 64-bit address per row pair; the +M32 neighbour is an immediate when kM is known
-        const float* p0 = value_b + (ptrdiff_t)(bm & ~31);
-        const float* p2 = p0 + (ptrdiff_t)(lv.W[l] * M32);
+        const VT* p0 = value_b + (ptrdiff_t)(bm & ~31);
+        const VT* p2 = p0 + (ptrdiff_t)(lv.W[l] * M32);
+        float v[C];
         if (bm & 1) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(p0));
+          RT::load(p0, v);
           const float w = a_hh * hw;
-          acc0 = fmaf(w, v.x, acc0); acc1 = fmaf(w, v.y, acc1); acc2 = fmaf(w, v.z, acc2); acc3 = fmaf(w, v.w, acc3);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
         }
         if (bm & 2) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(p0 + M32));
+          RT::load(p0 + M32, v);
           const float w = a_hh * lw;
-          acc0 = fmaf(w, v.x, acc0); acc1 = fmaf(w, v.y, acc1); acc2 = fmaf(w, v.z, acc2); acc3 = fmaf(w, v.w, acc3);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
         }
         if (bm & 4) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(p2));
+          RT::load(p2, v);
           const float w = a_lh * hw;
-          acc0 = fmaf(w, v.x, acc0); acc1 = fmaf(w, v.y, acc1); acc2 = fmaf(w, v.z, acc2); acc3 = fmaf(w, v.w, acc3);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
         }
         if (bm & 8) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(p2 + M32));
+          RT::load(p2 + M32, v);
           const float w = a_lh * lw;
-          acc0 = fmaf(w, v.x, acc0); acc1 = fmaf(w, v.y, acc1); acc2 = fmaf(w, v.z, acc2); acc3 = fmaf(w, v.w, acc3);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
         }
       }
-      st_stream_f4(out + qm * 32 + j * kC, make_float4(acc0, acc1, acc2, acc3));
+      RT::store_stream(out + qm * 32 + j * C, acc);
     }
     __syncwarp();
   }
 }
 
-// Reduce-scatter of v[0..7] over the 8 lanes of a group: returns, in lane j, the sum over the
-// group's lanes of v[j].  7 shuffles instead of the 24 that 8 separate butterflies would take.
-__device__ __forceinline__ float group_reduce_scatter8(const float (&v)[8], const int j,
-                                                       const unsigned amask) {
-  float a[4], b2[2];
-  const bool hi4 = j & 4, hi2 = j & 2, hi1 = j & 1;
+// Reduce-scatter of v[0..G) over the G lanes of a group: returns, in lane j, the sum over the
+// group's lanes of v[j].  G-1 shuffles instead of the G*log2(G) of G separate butterflies.
+template <int G>
+__device__ __forceinline__ float group_reduce_scatter(float (&v)[G], const int j, const unsigned amask) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float send = hi4 ? v[k] : v[k + 4];
-    const float keep = hi4 ? v[k + 4] : v[k];
-    a[k] = keep + __shfl_xor_sync(amask, send, 4);
-  }
+  for (int h = G / 2; h >= 1; h >>= 1) {
+    const bool hi = j & h;
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const float send = hi2 ? a[k] : a[k + 2];
-    const float keep = hi2 ? a[k + 2] : a[k];
-    b2[k] = keep + __shfl_xor_sync(amask, send, 2);
+    for (int k = 0; k < h; ++k) {
+      const float send = hi ? v[k] : v[k + h];
+      const float keep = hi ? v[k + h] : v[k];
+      v[k] = keep + __shfl_xor_sync(amask, send, h);
+    }
   }
-  const float send = hi1 ? b2[0] : b2[1];
-  const float keep = hi1 ? b2[1] : b2[0];
-  return keep + __shfl_xor_sync(amask, send, 1);
+  return v[0];
 }
 
 // ------------------------------------------------------------------------------------------
 // backward, atomic grad_value (REDG.E.ADD.F32x4); kScatter=false leaves grad_value alone
-// (deterministic mode computes it separately, msda_det.cuh)
+// (deterministic mode computes it separately, msda_det.cuh).  grad_out has value's type;
+// all three gradients are fp32.
 // ------------------------------------------------------------------------------------------
-template <int kL, int kP, int kM, bool kScatter>
+template <typename VT, int kL, int kP, int kM, bool kScatter>
 __global__ void __launch_bounds__(kThreads, MSDA_BWD_MINBLOCKS)
-msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict__ value,
+msda_bwd_d32_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                     const float* __restrict__ loc, const float* __restrict__ attw,
                     float* __restrict__ grad_value, float* __restrict__ grad_loc,
                     float* __restrict__ grad_attw, const int* __restrict__ order,
                     const int order_len, const __grid_constant__ MsdaLevels lv, const int S,
                     const int M_rt, const int Lq) {
   constexpr int LP = kL * kP;
-  using Cfg = D32Cfg<LP>;
+  using Cfg = D32Cfg<VT, LP>;
+  using RT = RowTraits<VT>;
+  constexpr int G = Cfg::G, C = Cfg::C;
   extern __shared__ float4 smem[];
   const int M = kM ? kM : M_rt;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane / kG, j = lane % kG;
+  const int g = lane / G, j = lane % G;
   const int m = blockIdx.x % M;
   const int tile = blockIdx.x / M;
   const int b = blockIdx.y;
   const int M32 = M * 32;
 
   float4* rec = smem + (warp * Cfg::GPW + g) * Cfg::REC_STRIDE;
-  const float* value_b = value + (size_t)b * S * M32 + j * kC;
-  const ptrdiff_t gdelta = grad_value - value;  // same element offsets in value and grad_value
+  const size_t img = (size_t)b * S * M32 + j * C;
+  const VT* value_b = value + img;
+  float* gvalue_b = grad_value + img;
 
 #pragma unroll 1
   for (int pass = 0; pass < Cfg::PASSES; ++pass) {
@@ -215,20 +273,21 @@ msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict_
     const bool active = q >= 0;
     const size_t qm = ((size_t)b * Lq + (active ? q : 0)) * M + m;
 
-    if (active) d32_decode_points<kL, kP>(loc, attw, qm, j, m, M, lv, rec);
+    if (active) d32_decode_points<G, kL, kP>(loc, attw, qm, j, m, M, lv, rec);
     __syncwarp();
     const unsigned amask = __ballot_sync(0xffffffffu, active);
 
     if (active) {
-      const float4 go = ld_stream_f4(grad_out + qm * 32 + j * kC);
-      // points are reduced in blocks of 8: lane j ends up owning point (8*blk + j) — the same
+      float go[C];
+      RT::load_stream(grad_out + qm * 32 + j * C, go);
+      // points are reduced in blocks of G: lane j ends up owning point (G*blk + j) — the same
       // point it decoded, so it also stores that point's gradients.
 #pragma unroll
       for (int blk = 0; blk < Cfg::KP; ++blk) {
-        float pgx[8], pgy[8], pga[8];
+        float pgx[G], pgy[G], pga[G];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int p = blk * 8 + i;
+        for (int i = 0; i < G; ++i) {
+          const int p = blk * G + i;
           pgx[i] = pgy[i] = pga[i] = 0.f;
           if (p < LP) {
             const int l = p / kP;
@@ -237,42 +296,40 @@ msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict_
             const float lh = r.y, lw = r.z, a = r.w;
             const float hh = 1.f - lh, hw = 1.f - lw;
             const float a_hh = a * hh, a_lh = a * lh;
-            const float* p0 = value_b + (ptrdiff_t)(bm & ~31);
-            const float* p2 = p0 + (ptrdiff_t)(lv.W[l] * M32);
+            const ptrdiff_t o0 = (ptrdiff_t)(bm & ~31);
+            const ptrdiff_t o2 = o0 + (ptrdiff_t)(lv.W[l] * M32);
             // per corner: gather the row, scatter corner weight x attention weight x grad_out into
             // grad_value (cuh:125,134,143,152), and dot the row with grad_out over this lane's channels
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-            if (bm & 1) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(p0));
-              if (kScatter) { const float t = a_hh * hw; red_add_f4(const_cast<float*>(p0) + gdelta, t * go.x, t * go.y, t * go.z, t * go.w); }
-              d0 = go.x * v.x + go.y * v.y + go.z * v.z + go.w * v.w;
-            }
-            if (bm & 2) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(p0 + M32));
-              if (kScatter) { const float t = a_hh * lw; red_add_f4(const_cast<float*>(p0) + gdelta + M32, t * go.x, t * go.y, t * go.z, t * go.w); }
-              d1 = go.x * v.x + go.y * v.y + go.z * v.z + go.w * v.w;
-            }
-            if (bm & 4) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(p2));
-              if (kScatter) { const float t = a_lh * hw; red_add_f4(const_cast<float*>(p2) + gdelta, t * go.x, t * go.y, t * go.z, t * go.w); }
-              d2 = go.x * v.x + go.y * v.y + go.z * v.z + go.w * v.w;
-            }
-            if (bm & 8) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(p2 + M32));
-              if (kScatter) { const float t = a_lh * lw; red_add_f4(const_cast<float*>(p2) + gdelta + M32, t * go.x, t * go.y, t * go.z, t * go.w); }
-              d3 = go.x * v.x + go.y * v.y + go.z * v.z + go.w * v.w;
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (bm & (1 << k)) {
+                const ptrdiff_t o = ((k & 2) ? o2 : o0) + ((k & 1) ? M32 : 0);
+                float v[C];
+                RT::load(value_b + o, v);
+                if (kScatter) {
+                  const float t = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
+#pragma unroll
+                  for (int c = 0; c < C; c += 4)
+                    red_add_f4(gvalue_b + o + c, t * go[c], t * go[c + 1], t * go[c + 2], t * go[c + 3]);
+                }
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) s = fmaf(go[c], v[c], s);
+                d[k] = s;
+              }
             }
             // grad_attn_weight = sum_c grad_out * bilinear(value)                      (cuh:156)
-            pga[i] = hh * (hw * d0 + lw * d1) + lh * (hw * d2 + lw * d3);
+            pga[i] = hh * (hw * d[0] + lw * d[1]) + lh * (hw * d[2] + lw * d[3]);
             // d/dx: W*a*(-hh v00 + hh v01 - lh v10 + lh v11); d/dy: H*a*(-hw v00 - lw v01 + hw v10 + lw v11)
-            pgx[i] = (a * (float)lv.W[l]) * (hh * (d1 - d0) + lh * (d3 - d2));  // (cuh:157)
-            pgy[i] = (a * (float)lv.H[l]) * (hw * (d2 - d0) + lw * (d3 - d1));  // (cuh:158)
+            pgx[i] = (a * (float)lv.W[l]) * (hh * (d[1] - d[0]) + lh * (d[3] - d[2]));  // (cuh:157)
+            pgy[i] = (a * (float)lv.H[l]) * (hw * (d[2] - d[0]) + lw * (d[3] - d[1]));  // (cuh:158)
           }
         }
-        const float gx = group_reduce_scatter8(pgx, j, amask);
-        const float gy = group_reduce_scatter8(pgy, j, amask);
-        const float ga = group_reduce_scatter8(pga, j, amask);
-        const int p = blk * 8 + j;
+        const float gx = group_reduce_scatter<G>(pgx, j, amask);
+        const float gy = group_reduce_scatter<G>(pgy, j, amask);
+        const float ga = group_reduce_scatter<G>(pga, j, amask);
+        const int p = blk * G + j;
         if (p < LP) {
           st_stream_f2(grad_loc + (qm * LP + p) * 2, make_float2(gx, gy));
           st_stream_f1(grad_attw + qm * LP + p, ga);
@@ -280,6 +337,149 @@ msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict_
       }
     }
     __syncwarp();
+  }
+}
+
+// ==========================================================================================
+// "split" variants for small problems (decoder cross-attention: a few thousand queries).
+// With one lane group per (query, head) the grid is too small to hide the latency of 16
+// dependent gather rounds, so here a whole WARP owns one (query, head): lane group g handles
+// points g, g+GPW, ... (4x / 8x more rows in flight per query), and the forward combines the
+// groups' partial sums with xor-shuffles.  Block = 4 warps = 4 consecutive queries of one head.
+// ==========================================================================================
+constexpr int kSplitThreads = 128;
+
+template <typename VT, int kL, int kP, int kM>
+__global__ void __launch_bounds__(kSplitThreads)
+msda_fwd_d32_split_kernel(const VT* __restrict__ value, const float* __restrict__ loc,
+                          const float* __restrict__ attw, VT* __restrict__ out,
+                          const __grid_constant__ MsdaLevels lv, const int S, const int M_rt, const int Lq) {
+  constexpr int LP = kL * kP;
+  using RT = RowTraits<VT>;
+  constexpr int G = RT::G, C = RT::C, GPW = 32 / G;
+  constexpr int NPG = (LP + GPW - 1) / GPW;  // points per lane group
+  __shared__ float4 smem[(kSplitThreads / 32) * (LP + 1)];
+  const int M = kM ? kM : M_rt;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / G, j = lane % G;
+  const int m = blockIdx.x % M;
+  const int q = (blockIdx.x / M) * (kSplitThreads / 32) + warp;
+  const int b = blockIdx.y;
+  const int M32 = M * 32;
+  if (q >= Lq) return;  // warp-uniform
+  float4* rec = smem + warp * (LP + 1);
+  const VT* value_b = value + (size_t)b * S * M32 + j * C;
+  const size_t qm = ((size_t)b * Lq + q) * M + m;
+  d32_decode_points<32, kL, kP>(loc, attw, qm, lane, m, M, lv, rec);
+  __syncwarp();
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPG; ++i) {
+    const int p = g + GPW * i;
+    if (p < LP) {
+      const int l = p / kP;
+      const float4 r = rec[p];
+      const int bm = __float_as_int(r.x);
+      const float lh = r.y, lw = r.z, a = r.w;
+      const float a_hh = a * (1.f - lh), a_lh = a * lh, hw = 1.f - lw;
+      const VT* p0 = value_b + (ptrdiff_t)(bm & ~31);
+      const VT* p2 = p0 + (ptrdiff_t)(lv.W[l] * M32);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (bm & (1 << k)) {
+          float v[C];
+          RT::load(((k & 2) ? p2 : p0) + ((k & 1) ? M32 : 0), v);
+          const float w = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int s = G; s < 32; s <<= 1)
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], s);
+  if (g == 0) RT::store_stream(out + qm * 32 + j * C, acc);
+}
+
+template <typename VT, int kL, int kP, int kM, bool kScatter>
+__global__ void __launch_bounds__(kSplitThreads)
+msda_bwd_d32_split_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
+                          const float* __restrict__ loc, const float* __restrict__ attw,
+                          float* __restrict__ grad_value, float* __restrict__ grad_loc,
+                          float* __restrict__ grad_attw, const __grid_constant__ MsdaLevels lv,
+                          const int S, const int M_rt, const int Lq) {
+  constexpr int LP = kL * kP;
+  using RT = RowTraits<VT>;
+  constexpr int G = RT::G, C = RT::C, GPW = 32 / G;
+  constexpr int NPG = (LP + GPW - 1) / GPW;
+  __shared__ float4 smem[(kSplitThreads / 32) * (LP + 1)];
+  const int M = kM ? kM : M_rt;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / G, j = lane % G;
+  const int m = blockIdx.x % M;
+  const int q = (blockIdx.x / M) * (kSplitThreads / 32) + warp;
+  const int b = blockIdx.y;
+  const int M32 = M * 32;
+  if (q >= Lq) return;
+  float4* rec = smem + warp * (LP + 1);
+  const size_t img = (size_t)b * S * M32 + j * C;
+  const VT* value_b = value + img;
+  float* gvalue_b = grad_value + img;
+  const size_t qm = ((size_t)b * Lq + q) * M + m;
+  d32_decode_points<32, kL, kP>(loc, attw, qm, lane, m, M, lv, rec);
+  __syncwarp();
+  float go[C];
+  RT::load_stream(grad_out + qm * 32 + j * C, go);
+#pragma unroll
+  for (int i = 0; i < NPG; ++i) {
+    const int p = g + GPW * i;
+    float ga = 0.f, gx = 0.f, gy = 0.f;
+    if (p < LP) {
+      const int l = p / kP;
+      const float4 r = rec[p];
+      const int bm = __float_as_int(r.x);
+      const float lh = r.y, lw = r.z, a = r.w;
+      const float hh = 1.f - lh, hw = 1.f - lw;
+      const float a_hh = a * hh, a_lh = a * lh;
+      const ptrdiff_t o0 = (ptrdiff_t)(bm & ~31);
+      const ptrdiff_t o2 = o0 + (ptrdiff_t)(lv.W[l] * M32);
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (bm & (1 << k)) {
+          const ptrdiff_t o = ((k & 2) ? o2 : o0) + ((k & 1) ? M32 : 0);
+          float v[C];
+          RT::load(value_b + o, v);
+          if (kScatter) {
+            const float t = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
+#pragma unroll
+            for (int c = 0; c < C; c += 4)
+              red_add_f4(gvalue_b + o + c, t * go[c], t * go[c + 1], t * go[c + 2], t * go[c + 3]);
+          }
+          float sdot = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) sdot = fmaf(go[c], v[c], sdot);
+          d[k] = sdot;
+        }
+      }
+      ga = hh * (hw * d[0] + lw * d[1]) + lh * (hw * d[2] + lw * d[3]);
+      gx = (a * (float)lv.W[l]) * (hh * (d[1] - d[0]) + lh * (d[3] - d[2]));
+      gy = (a * (float)lv.H[l]) * (hw * (d[2] - d[0]) + lw * (d[3] - d[1]));
+    }
+#pragma unroll
+    for (int s = G / 2; s >= 1; s >>= 1) {
+      ga += __shfl_xor_sync(0xffffffffu, ga, s);
+      gx += __shfl_xor_sync(0xffffffffu, gx, s);
+      gy += __shfl_xor_sync(0xffffffffu, gy, s);
+    }
+    if (j == 0 && p < LP) {
+      st_stream_f2(grad_loc + (qm * LP + p) * 2, make_float2(gx, gy));
+      st_stream_f1(grad_attw + qm * LP + p, ga);
+    }
   }
 }
 

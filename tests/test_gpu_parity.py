@@ -40,14 +40,16 @@ def test_extension_is_loaded_from_the_tree():
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-@pytest.mark.parametrize("force_generic", [False, True])
-def test_golden_forward_backward(case, force_generic):
+@pytest.mark.parametrize("path", ["auto", "tiled", "generic"])
+def test_golden_forward_backward(case, path):
+    """auto = what the library picks (warp-per-query "split" kernels at these sizes for D=32);
+    tiled = the lane-group-per-query kernels used for large problems; generic = any-shape kernels."""
     from richsem_b200 import _capi
 
     g = load_golden(case)
     f64 = g["value"].dtype == torch.float64
     v, shp, st, loc, w, go = _to_dev(g)
-    flags = _capi.FLAG_FORCE_GENERIC if force_generic else 0
+    flags = {"auto": 0, "tiled": _capi.FLAG_NO_SPLIT, "generic": _capi.FLAG_FORCE_GENERIC}[path]
     out = _ext().ms_deform_attn_forward(v, shp, st, loc, w, 64, _flags=flags)
     gv, gl, ga = _ext().ms_deform_attn_backward(v, shp, st, loc, w, go, 64, _flags=flags)
     ft, bt = (1e-12, 1e-11) if f64 else (FWD_TOL, BWD_TOL)
@@ -145,12 +147,15 @@ def test_query_order_does_not_change_results(monkeypatch):
 
     shapes = [(20, 31), (10, 16), (5, 8), (3, 4)]
     i = syn.make_inputs("E", 2, shapes, "cuda:0", seed=3)
+    from richsem_b200 import _capi
+
     args = (i["value"], i["shapes"], i["starts"], i["loc"], i["attw"])
-    a = _ext().ms_deform_attn_forward(*args, 64)
-    ga = _ext().ms_deform_attn_backward(*args, i["grad_out"], 64)
+    nosplit = _capi.FLAG_NO_SPLIT
+    a = _ext().ms_deform_attn_forward(*args, 64, _flags=nosplit)
+    ga = _ext().ms_deform_attn_backward(*args, i["grad_out"], 64, _flags=nosplit)
     monkeypatch.setenv("MSDA_B200_QUERY_ORDER", "natural")
-    b = _ext().ms_deform_attn_forward(*args, 64)
-    gb = _ext().ms_deform_attn_backward(*args, i["grad_out"], 64)
+    b = _ext().ms_deform_attn_forward(*args, 64, _flags=nosplit)
+    gb = _ext().ms_deform_attn_backward(*args, i["grad_out"], 64, _flags=nosplit)
     assert torch.equal(a, b)                       # forward: each (q, m) is computed by one lane group
     assert torch.equal(ga[1], gb[1]) and torch.equal(ga[2], gb[2])
     assert rel_err(ga[0], gb[0]) < 1e-5            # grad_value: atomic order differs
@@ -205,15 +210,18 @@ def test_deterministic_mode_is_bitwise_reproducible_and_close_to_atomic():
     assert rel_err(e1[0], e3[0]) < BWD_TOL
 
 
-def test_bf16_value_variant(c_oracle):
-    from richsem_b200 import synthetic as syn
+@pytest.mark.parametrize("path", ["auto", "tiled", "generic"])
+def test_bf16_value_variant(c_oracle, path):
+    from richsem_b200 import _capi, synthetic as syn
 
+    flags = {"auto": 0, "tiled": _capi.FLAG_NO_SPLIT, "generic": _capi.FLAG_FORCE_GENERIC}[path]
     shapes = syn.level_shapes(800, 1333)
     i = syn.make_inputs("Dn", 2, shapes, "cuda:0", seed=31, lq=1100)
     vb, gob = i["value"].bfloat16(), i["grad_out"].bfloat16()
-    out = _ext().ms_deform_attn_forward(vb, i["shapes"], i["starts"], i["loc"], i["attw"], 64)
+    out = _ext().ms_deform_attn_forward(vb, i["shapes"], i["starts"], i["loc"], i["attw"], 64, _flags=flags)
     assert out.dtype == torch.bfloat16
-    gv, gl, ga = _ext().ms_deform_attn_backward(vb, i["shapes"], i["starts"], i["loc"], i["attw"], gob, 64)
+    gv, gl, ga = _ext().ms_deform_attn_backward(vb, i["shapes"], i["starts"], i["loc"], i["attw"], gob, 64,
+                                                _flags=flags)
     assert gv.dtype == torch.float32 and gl.dtype == torch.float32 and ga.dtype == torch.float32
     # oracle in fp32 on the UNROUNDED inputs: the 1e-2 budget covers bf16 storage of value/out/grad_out
     v, loc, w, go = (i[k].cpu() for k in ("value", "loc", "attw", "grad_out"))
