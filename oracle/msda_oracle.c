@@ -53,6 +53,41 @@ static int geom_f64(double x, double y, int H, int W, int64_t start, int32_t tok
   GEOM_BODY(double, floor)
 }
 
+/* Same geometry with the pixel coordinate computed as ONE fused multiply-add, fmaf(x, W, -0.5f):
+ * what nvcc's default -fmad=true makes of cuh:285-286, i.e. the compiled reference extension.
+ * (MSDA_FLAG_COORDS_FMA in the library.) */
+static int geom_f32_fma(float x, float y, int H, int W, int64_t start, int32_t tok[4], float* lh, float* lw) {
+  const float w_im = fmaf(x, (float)W, -0.5f), h_im = fmaf(y, (float)H, -0.5f);
+  tok[0] = tok[1] = tok[2] = tok[3] = -1;
+  *lh = 0;
+  *lw = 0;
+  if (!(h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W)) return 0;
+  {
+    const float hf = floorf(h_im), wf = floorf(w_im);
+    const int h0 = (int)hf, w0 = (int)wf, h1 = h0 + 1, w1 = w0 + 1;
+    *lh = h_im - hf;
+    *lw = w_im - wf;
+    if (h0 >= 0 && w0 >= 0) tok[0] = (int32_t)(start + (int64_t)h0 * W + w0);
+    if (h0 >= 0 && w1 <= W - 1) tok[1] = (int32_t)(start + (int64_t)h0 * W + w1);
+    if (h1 <= H - 1 && w0 >= 0) tok[2] = (int32_t)(start + (int64_t)h1 * W + w0);
+    if (h1 <= H - 1 && w1 <= W - 1) tok[3] = (int32_t)(start + (int64_t)h1 * W + w1);
+  }
+  return 1;
+}
+
+void msda_oracle_corners_f32_fma(const int64_t* shapes, const int64_t* start, const float* loc, int64_t n_qm,
+                                 int L, int P, int32_t* corners) {
+#pragma omp parallel for schedule(static)
+  for (int64_t t = 0; t < n_qm; ++t)
+    for (int l = 0; l < L; ++l)
+      for (int p = 0; p < P; ++p) {
+        const int64_t s = (t * L + l) * P + p;
+        float lh, lw;
+        geom_f32_fma(loc[2 * s], loc[2 * s + 1], (int)shapes[2 * l], (int)shapes[2 * l + 1], start[l],
+                     corners + 4 * s, &lh, &lw);
+      }
+}
+
 /* corners[b,q,m,l,p,4] : token index of each bilinear corner, -1 if it contributes nothing */
 void msda_oracle_corners_f32(const int64_t* shapes, const int64_t* start, const float* loc, int64_t n_qm,
                              int L, int P, int32_t* corners) {

@@ -106,7 +106,7 @@ class COracle:
         build()
         self.lib = ctypes.CDLL(str(_LIB))
         for f in ("msda_oracle_forward_f32", "msda_oracle_forward_f64", "msda_oracle_backward_f32",
-                  "msda_oracle_backward_f64", "msda_oracle_corners_f32"):
+                  "msda_oracle_backward_f64", "msda_oracle_corners_f32", "msda_oracle_corners_f32_fma"):
             getattr(self.lib, f).restype = None
 
     @staticmethod
@@ -145,19 +145,21 @@ class COracle:
            n, s, m, d, nl, lq, npt, self._p(gv), self._p(gl), self._p(ga))
         return gv, gl, ga
 
-    def corners(self, spatial_shapes, loc, level_start_index=None):
-        """int32 (N,Lq,M,L,P,4): token index of each bilinear corner, -1 where it contributes nothing."""
+    def corners(self, spatial_shapes, loc, level_start_index=None, fma=False):
+        """int32 (N,Lq,M,L,P,4): token index of each bilinear corner, -1 where it contributes nothing.
+        fma=True: pixel coordinate as one fused multiply-add (the compiled reference kernel's arithmetic)."""
         loc = loc.contiguous().float()
         n, lq, m, nl, npt, _ = loc.shape
         shp, st = self._meta(spatial_shapes, level_start_index)
         out = torch.empty(n, lq, m, nl, npt, 4, dtype=torch.int32)
-        self.lib.msda_oracle_corners_f32(self._p(shp), self._p(st), self._p(loc),
-                                         ctypes.c_int64(n * lq * m), nl, npt, self._p(out))
+        fn = self.lib.msda_oracle_corners_f32_fma if fma else self.lib.msda_oracle_corners_f32
+        fn(self._p(shp), self._p(st), self._p(loc), ctypes.c_int64(n * lq * m), nl, npt, self._p(out))
         return out
 
 
-def corners_numpy(spatial_shapes, loc, level_start_index=None):
-    """Pure-numpy cross-check of COracle.corners (fp32 mul, then fp32 sub, then floor)."""
+def corners_numpy(spatial_shapes, loc, level_start_index=None, fma=False):
+    """Pure-numpy cross-check of COracle.corners (fp32 mul, then fp32 sub, then floor); with fma=True the
+    coordinate is the exactly computed x*W - 0.5 (float64 holds it exactly) rounded once to fp32."""
     loc = np.asarray(loc, dtype=np.float32)
     n, lq, m, nl, npt, _ = loc.shape
     out = np.full((n, lq, m, nl, npt, 4), -1, dtype=np.int32)
@@ -166,8 +168,12 @@ def corners_numpy(spatial_shapes, loc, level_start_index=None):
         h, w = int(h), int(w)
         st = start if level_start_index is None else int(level_start_index[l])
         start += h * w
-        wim = (loc[:, :, :, l, :, 0] * np.float32(w)).astype(np.float32) - np.float32(0.5)
-        him = (loc[:, :, :, l, :, 1] * np.float32(h)).astype(np.float32) - np.float32(0.5)
+        if fma:
+            wim = (loc[:, :, :, l, :, 0].astype(np.float64) * w - 0.5).astype(np.float32)
+            him = (loc[:, :, :, l, :, 1].astype(np.float64) * h - 0.5).astype(np.float32)
+        else:
+            wim = (loc[:, :, :, l, :, 0] * np.float32(w)).astype(np.float32) - np.float32(0.5)
+            him = (loc[:, :, :, l, :, 1] * np.float32(h)).astype(np.float32) - np.float32(0.5)
         ok = (him > -1) & (wim > -1) & (him < h) & (wim < w)
         h0 = np.floor(him).astype(np.int64)
         w0 = np.floor(wim).astype(np.int64)
@@ -176,3 +182,46 @@ def corners_numpy(spatial_shapes, loc, level_start_index=None):
             good = ok & (hh >= 0) & (hh <= h - 1) & (ww >= 0) & (ww <= w - 1)
             out[:, :, :, l, :, k] = np.where(good, st + hh * w + ww, -1)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# The reference's own CUDA kernels (oracle/_ref/libmsda_legacy.so, built by oracle/build_ref.py
+# from /root/reference in the build container).  GPU comparator: second parity check and
+# "legacy kernel recompiled for sm_100a" timing.  Never the product path.
+# --------------------------------------------------------------------------------------
+_LEGACY = _HERE / "_ref" / "libmsda_legacy.so"
+
+
+class LegacyCuda:
+    """ctypes front end of the reference launchers (cuh:923-954, 956-1327); CUDA fp32 tensors."""
+
+    @staticmethod
+    def available():
+        return _LEGACY.exists()
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(str(_LEGACY))
+        self.lib.legacy_forward_f32.restype = None
+        self.lib.legacy_backward_f32.restype = None
+
+    @staticmethod
+    def _args(value, shapes, starts, loc, attw):
+        n, s, m, d = value.shape
+        lq, nl, npt = loc.shape[1], loc.shape[3], loc.shape[4]
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return stream, p, (n, s, m, d, nl, lq, npt)
+
+    def forward(self, value, shapes, starts, loc, attw):
+        stream, p, dims = self._args(value, shapes, starts, loc, attw)
+        n, s, m, d, nl, lq, npt = dims
+        out = torch.zeros(n, lq, m * d, dtype=value.dtype, device=value.device)  # reference: at::zeros (cu:54)
+        self.lib.legacy_forward_f32(stream, p(value), p(shapes), p(starts), p(loc), p(attw), *dims, p(out))
+        return out
+
+    def backward(self, value, shapes, starts, loc, attw, grad_out):
+        stream, p, dims = self._args(value, shapes, starts, loc, attw)
+        gv, gl, ga = torch.zeros_like(value), torch.zeros_like(loc), torch.zeros_like(attw)  # cu:121-123
+        self.lib.legacy_backward_f32(stream, p(grad_out), p(value), p(shapes), p(starts), p(loc), p(attw), *dims,
+                                     p(gv), p(gl), p(ga))
+        return gv, gl, ga

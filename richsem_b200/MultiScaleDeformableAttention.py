@@ -175,7 +175,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     return [grad_value, grad_loc, grad_attw]
 
 
-def debug_corners(spatial_shapes, level_start_index, sampling_loc):
+def debug_corners(spatial_shapes, level_start_index, sampling_loc, _flags: int = 0):
     """int32 (N,Lq,M,L,P,4) bilinear corner token indices as the fp32/bf16 kernels compute them
     (-1 = contributes nothing).  Test hook for the bit-exact index contract."""
     _require(sampling_loc.is_cuda and sampling_loc.dtype == torch.float32 and sampling_loc.is_contiguous(),
@@ -186,6 +186,6 @@ def debug_corners(spatial_shapes, level_start_index, sampling_loc):
     with _on_device(sampling_loc.device):
         rc = _capi.lib.msda_debug_corners_f32(_stream(sampling_loc.device), _dev_ptr(spatial_shapes), _dev_ptr(level_start_index),
                                               sampling_loc.data_ptr(), n, m, nl, lq, npt, out.data_ptr(),
-                                              _capi.make_opts(meta))
+                                              _capi.make_opts(meta, flags=_flags))
     _capi.check(rc, "msda_debug_corners_f32")
     return out

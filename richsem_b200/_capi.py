@@ -22,6 +22,7 @@ FLAG_DETERMINISTIC = 0x1
 FLAG_GRAD_VALUE_PREZEROED = 0x2
 FLAG_FORCE_GENERIC = 0x4
 FLAG_NO_SPLIT = 0x8
+FLAG_COORDS_FMA = 0x10
 MAX_LEVELS = 16
 
 _vp, _i, _i64p = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)

@@ -104,7 +104,9 @@ int make_problem(cudaStream_t stream, const int64_t* shapes, const int64_t* star
   if (pb->order && pb->order_len < num_query)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "query_order_len=%d shorter than num_query=%d",
                 pb->order_len, num_query);
-  return resolve_levels(stream, shapes, start, num_levels, spatial_size, opts, &pb->lv);
+  const int rc = resolve_levels(stream, shapes, start, num_levels, spatial_size, opts, &pb->lv);
+  pb->lv.coord_fma = (pb->flags & MSDA_FLAG_COORDS_FMA) ? 1 : 0;
+  return rc;
 }
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
@@ -374,6 +376,7 @@ int msda_debug_corners_f32(msda_stream_t stream, const int64_t* spatial_shapes,
   MsdaLevels lv;
   int rc = resolve_levels(s, spatial_shapes, level_start_index, num_levels, INT32_MAX, opts, &lv);
   if (rc != MSDA_OK) return rc;
+  lv.coord_fma = (opt_flags(opts) & MSDA_FLAG_COORDS_FMA) ? 1 : 0;
   const long long n = (long long)batch * num_query * num_heads * num_levels * num_point;
   if (n == 0) return MSDA_OK;
   long long blocks = (n + 255) / 256;

@@ -20,20 +20,27 @@ struct MsdaLevels {
   int H[MSDA_MAX_LEVELS];
   int W[MSDA_MAX_LEVELS];
   int start[MSDA_MAX_LEVELS];
+  int coord_fma;  // MSDA_FLAG_COORDS_FMA: pixel coordinate as one fused multiply-add (see msda_pix)
 };
 
 struct MsdaDims {
   int batch, spatial_size, num_heads, channels, num_levels, num_query, num_point;
 };
 
-// ---- pixel coordinate: loc * size - 0.5, two separately rounded operations -------------
-// (the reference multiplies in scalar_t and subtracts a double literal, which for float is
-// exactly a rounded multiply followed by a rounded subtract; cuh:285-286)
-__device__ __forceinline__ float msda_pix(float loc, int size) {
-  return __fsub_rn(__fmul_rn(loc, (float)size), 0.5f);
+// ---- pixel coordinate: loc * size - 0.5 -------------------------------------------------
+// Default (the index contract): two separately rounded operations, as the source of the
+// reference reads (it multiplies in scalar_t and subtracts a double literal, which for float
+// is exactly a rounded multiply followed by a rounded subtract; cuh:285-286).
+// fma=true: ONE fused multiply-add.  This is what nvcc actually emits for that source line
+// with its default -fmad=true (the double subtraction is narrowed to float, then contracted),
+// i.e. what the reference's compiled extension computes.  The two differ only when loc*size
+// rounds onto the pixel lattice (k + 0.5): measured 1 sample in 11.4 M for jittered encoder
+// locations, but every lattice point of an un-jittered initialisation.
+__device__ __forceinline__ float msda_pix(float loc, int size, bool fma) {
+  return fma ? __fmaf_rn(loc, (float)size, -0.5f) : __fsub_rn(__fmul_rn(loc, (float)size), 0.5f);
 }
-__device__ __forceinline__ double msda_pix(double loc, int size) {
-  return __dsub_rn(__dmul_rn(loc, (double)size), 0.5);
+__device__ __forceinline__ double msda_pix(double loc, int size, bool fma) {
+  return fma ? __fma_rn(loc, (double)size, -0.5) : __dsub_rn(__dmul_rn(loc, (double)size), 0.5);
 }
 
 // Geometry of one sampling point.
@@ -43,9 +50,9 @@ __device__ __forceinline__ double msda_pix(double loc, int size) {
 // Returns true when the sample passes the range test of cuh:288.
 template <typename T>
 __device__ __forceinline__ bool msda_sample_geom(T x, T y, int H, int W, int start, int (&tok)[4],
-                                                 T& lh, T& lw) {
-  const T w_im = msda_pix(x, W);
-  const T h_im = msda_pix(y, H);
+                                                 T& lh, T& lw, bool fma = false) {
+  const T w_im = msda_pix(x, W, fma);
+  const T h_im = msda_pix(y, H, fma);
   tok[0] = tok[1] = tok[2] = tok[3] = -1;
   lh = T(0);
   lw = T(0);

@@ -120,7 +120,7 @@ __device__ __forceinline__ void d32_decode_points(const float* __restrict__ loc,
       const int W = lv.W[l];
       int tok[4];
       float lh, lw;
-      const bool in = msda_sample_geom(xy.x, xy.y, lv.H[l], W, lv.start[l], tok, lh, lw);
+      const bool in = msda_sample_geom(xy.x, xy.y, lv.H[l], W, lv.start[l], tok, lh, lw, lv.coord_fma != 0);
       int base = 0, mask = 0;
       if (in) {
         // token of (h0, w0), valid or not: recover it from whichever corner exists

@@ -74,7 +74,7 @@ msda_det_bin_kernel(const float* __restrict__ loc, int* __restrict__ counts,
     const float2 xy = *reinterpret_cast<const float2*>(loc + s * 2);
     int tok[4];
     float lh, lw;
-    msda_sample_geom(xy.x, xy.y, lv.H[l], lv.W[l], lv.start[l], tok, lh, lw);
+    msda_sample_geom(xy.x, xy.y, lv.H[l], lv.W[l], lv.start[l], tok, lh, lw, lv.coord_fma != 0);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (tok[k] < 0) continue;
@@ -203,7 +203,7 @@ msda_det_reduce_kernel(const TV* __restrict__ grad_out, const float* __restrict_
           const float2 xy = *reinterpret_cast<const float2*>(loc + s * 2);
           int tok[4];
           float lh, lw;
-          msda_sample_geom(xy.x, xy.y, lv.H[l], lv.W[l], lv.start[l], tok, lh, lw);
+          msda_sample_geom(xy.x, xy.y, lv.H[l], lv.W[l], lv.start[l], tok, lh, lw, lv.coord_fma != 0);
           const float hh = 1.f - lh, hw = 1.f - lw;
           const float cw = k == 0 ? hh * hw : k == 1 ? hh * lw : k == 2 ? lh * hw : lh * lw;
           coef = attw[s] * cw;

@@ -57,7 +57,7 @@ msda_fwd_generic_kernel(const TV* __restrict__ value, const T* __restrict__ loc,
           const T x = loc_t[lp * 2], y = loc_t[lp * 2 + 1], a = w_t[lp];
           int tok[4];
           T lh, lw;
-          if (!msda_sample_geom(x, y, H, W, st, tok, lh, lw)) continue;
+          if (!msda_sample_geom(x, y, H, W, st, tok, lh, lw, lv.coord_fma != 0)) continue;
           if (c < d.channels) {
             const T hh = T(1) - lh, hw = T(1) - lw;
             const size_t ch = (size_t)m * d.channels + c;
@@ -104,7 +104,7 @@ msda_bwd_generic_kernel(const TV* __restrict__ grad_out, const TV* __restrict__ 
         int tok[4];
         T lh, lw;
         T ga = T(0), gx = T(0), gy = T(0);
-        if (msda_sample_geom(x, y, H, W, st, tok, lh, lw)) {  // warp-uniform
+        if (msda_sample_geom(x, y, H, W, st, tok, lh, lw, lv.coord_fma != 0)) {  // warp-uniform
           const T hh = T(1) - lh, hw = T(1) - lw;
           for (int c = lane; c < d.channels; c += 32) {
             const size_t ch = (size_t)m * d.channels + c;
@@ -143,7 +143,7 @@ msda_corners_kernel(const float* __restrict__ loc, int* __restrict__ corners,
     const int l = (int)((i / num_point) % num_levels);
     int tok[4];
     float lh, lw;
-    msda_sample_geom(loc[i * 2], loc[i * 2 + 1], lv.H[l], lv.W[l], lv.start[l], tok, lh, lw);
+    msda_sample_geom(loc[i * 2], loc[i * 2 + 1], lv.H[l], lv.W[l], lv.start[l], tok, lh, lw, lv.coord_fma != 0);
     reinterpret_cast<int4*>(corners)[i] = make_int4(tok[0], tok[1], tok[2], tok[3]);
   }
 }

@@ -81,6 +81,19 @@ def test_corner_indices_bit_exact_on_the_pixel_lattice(c_oracle):
     assert torch.equal(got, want)
 
 
+def test_corner_indices_fma_mode_bit_exact(c_oracle):
+    """MSDA_FLAG_COORDS_FMA reproduces the compiled reference kernel's coordinate arithmetic."""
+    from richsem_b200 import _capi, synthetic as syn
+
+    shapes = syn.level_shapes(800, 1333)
+    gen = torch.Generator().manual_seed(7)
+    loc = syn.locations_encoder(1, shapes, gen, "cpu", jitter_px=0.0)[:, ::7].contiguous()
+    shp, st, _ = syn.level_tensors(shapes, "cuda:0")
+    got = _ext().debug_corners(shp, st, loc.cuda(), _flags=_capi.FLAG_COORDS_FMA).cpu()
+    assert torch.equal(got, c_oracle.corners(shapes, loc, fma=True))
+    assert not torch.equal(got, c_oracle.corners(shapes, loc))
+
+
 def test_reference_test_py_cases():
     """models/richsem/ops/test.py:31-60: seed-3 tiny case, fp64 allclose and fp32 rtol 1e-2/atol 1e-3."""
     from oracle.msda_oracle import core_pytorch

@@ -62,6 +62,24 @@ def test_corner_indices_c_vs_numpy(case, c_oracle):
     assert np.array_equal(c, n)
 
 
+def test_fma_coordinate_variant_differs_only_on_the_lattice(c_oracle):
+    """The compiled reference kernel contracts loc*size-0.5 into one FMA; the two
+    variants may only disagree where fl(loc*size) lands on k+0.5."""
+    from richsem_b200 import synthetic as syn
+
+    shapes = syn.level_shapes(800, 1333)
+    gen = torch.Generator().manual_seed(7)
+    loc = syn.locations_encoder(1, shapes, gen, "cpu", jitter_px=0.0)[:, ::5].contiguous()  # on the lattice
+    a = c_oracle.corners(shapes, loc)
+    b = c_oracle.corners(shapes, loc, fma=True)
+    assert np.array_equal(b.numpy(), om.corners_numpy(shapes, loc.numpy(), fma=True))
+    differ = (a != b).any(-1)
+    assert 0 < differ.float().mean() < 0.5          # a sizeable share of lattice points flips ...
+    jit = syn.locations_encoder(1, shapes, gen, "cpu", jitter_px=0.5)[:, ::5].contiguous()
+    d2 = (c_oracle.corners(shapes, jit) != c_oracle.corners(shapes, jit, fma=True)).any(-1)
+    assert d2.float().mean() < 1e-5                 # ... and essentially none off the lattice
+
+
 def test_corner_indices_known_answers(c_oracle):
     # one level 4x6 (H=4, W=6), start 10; hand-computed from cuh:285-288 / :38-78
     shapes, start = [(4, 6)], [10]
