@@ -68,6 +68,8 @@ extern "C" {
 #define MSDA_FLAG_FORCE_GENERIC 0x4u          /* bypass the D=32 fast kernels (testing)                             */
 #define MSDA_FLAG_COORDS_FMA 0x10u             /* pixel coordinate = fma(loc, size, -0.5): what nvcc -fmad=true makes of
                                                  cuh:285-286, i.e. the compiled reference; default is mul-then-sub  */
+#define MSDA_FLAG_NO_AGGREGATE 0x20u           /* backward: never pre-aggregate grad_value on chip (comparison)    */
+#define MSDA_FLAG_AGGREGATE 0x40u              /* backward: pre-aggregate even without a query_order (testing)     */
 #define MSDA_FLAG_NO_SPLIT 0x8u               /* small problems: keep the lane-group-per-query kernels (testing)    */
 
 typedef void* msda_stream_t; /* cudaStream_t */

@@ -23,6 +23,8 @@ FLAG_GRAD_VALUE_PREZEROED = 0x2
 FLAG_FORCE_GENERIC = 0x4
 FLAG_NO_SPLIT = 0x8
 FLAG_COORDS_FMA = 0x10
+FLAG_NO_AGGREGATE = 0x20
+FLAG_AGGREGATE = 0x40
 MAX_LEVELS = 16
 
 _vp, _i, _i64p = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)
@@ -153,18 +155,29 @@ _order_cache: dict = {}
 PATCH = 8  # queries are tiled in PATCH x PATCH pixel patches per level; 64 = kTileQ of the kernels
 
 
-def build_patch_order(shapes, starts):
-    """Permutation of the S encoder tokens that visits each level in 8x8 pixel patches (row-major
-    inside a patch).  A thread block takes 64 consecutive entries, i.e. one patch (edge patches are
-    smaller, so later blocks straddle two neighbouring patches)."""
+def build_patch_order(shapes, starts, pad=False):
+    """Order of the S encoder tokens that visits each level in 8x8 pixel patches (row-major inside a
+    patch).  A thread block takes 64 consecutive entries.
+    pad=False: a permutation of [0, S); edge patches are smaller, so later blocks straddle two
+               neighbouring patches.
+    pad=True:  every patch occupies exactly 64 entries, missing pixels are -1 (skipped by the
+               kernels), so that one block = one patch everywhere (tighter windows for the L1 and
+               for the on-chip grad_value aggregation, at the price of some idle lane groups)."""
     import numpy as np
 
     parts = []
     for (h, w), st in zip(shapes, starts):
-        ys, xs = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
-        key = ((ys // PATCH) * ((w + PATCH - 1) // PATCH) + xs // PATCH) * (PATCH * PATCH) + (ys % PATCH) * PATCH + xs % PATCH
-        idx = np.argsort(key.ravel(), kind="stable")
-        parts.append(st + idx)
+        if not pad:
+            ys, xs = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+            key = ((ys // PATCH) * ((w + PATCH - 1) // PATCH) + xs // PATCH) * (PATCH * PATCH) \
+                + (ys % PATCH) * PATCH + xs % PATCH
+            parts.append(st + np.argsort(key.ravel(), kind="stable"))
+        else:
+            hp, wp = (h + PATCH - 1) // PATCH * PATCH, (w + PATCH - 1) // PATCH * PATCH
+            ys, xs = np.meshgrid(np.arange(hp), np.arange(wp), indexing="ij")
+            tok = np.where((ys < h) & (xs < w), st + ys * w + xs, -1)
+            tok = tok.reshape(hp // PATCH, PATCH, wp // PATCH, PATCH).transpose(0, 2, 1, 3).reshape(-1)
+            parts.append(tok)
     return np.concatenate(parts).astype(np.int32)
 
 
@@ -179,10 +192,11 @@ def query_order(meta: LevelMeta, num_query: int, device) -> "torch.Tensor | None
         if st != acc:
             return None
         acc += h * w
-    key = (meta.shapes, str(device))
+    pad = os.environ.get("MSDA_B200_ORDER_PAD", "1") not in ("", "0")
+    key = (meta.shapes, str(device), pad)
     t = _order_cache.get(key)
     if t is None:
-        t = torch.from_numpy(build_patch_order(meta.shapes, meta.starts)).to(device)
+        t = torch.from_numpy(build_patch_order(meta.shapes, meta.starts, pad=pad)).to(device)
         if len(_order_cache) > 64:
             _order_cache.clear()
         _order_cache[key] = t

@@ -49,19 +49,20 @@ __device__ __forceinline__ double msda_pix(double loc, int size, bool fma) {
 //   lh, lw  fractional parts (0 when the whole sample is skipped).
 // Returns true when the sample passes the range test of cuh:288.
 template <typename T>
-__device__ __forceinline__ bool msda_sample_geom(T x, T y, int H, int W, int start, int (&tok)[4],
-                                                 T& lh, T& lw, bool fma = false) {
+__device__ __forceinline__ bool msda_sample_geom_hw(T x, T y, int H, int W, int start, int (&tok)[4],
+                                                    T& lh, T& lw, int& h0, int& w0, bool fma = false) {
   const T w_im = msda_pix(x, W, fma);
   const T h_im = msda_pix(y, H, fma);
   tok[0] = tok[1] = tok[2] = tok[3] = -1;
   lh = T(0);
   lw = T(0);
+  h0 = w0 = 0;
   // NaN coordinates fail every comparison and are skipped, as in the reference.
   if (!(h_im > T(-1) && w_im > T(-1) && h_im < T(H) && w_im < T(W))) return false;
   const T hf = floor(h_im);
   const T wf = floor(w_im);
-  const int h0 = (int)hf;
-  const int w0 = (int)wf;
+  h0 = (int)hf;
+  w0 = (int)wf;
   lh = h_im - hf;
   lw = w_im - wf;
   const bool h0ok = h0 >= 0, w0ok = w0 >= 0;
@@ -72,6 +73,13 @@ __device__ __forceinline__ bool msda_sample_geom(T x, T y, int H, int W, int sta
   if (h1ok && w0ok) tok[2] = base + W;
   if (h1ok && w1ok) tok[3] = base + W + 1;
   return true;
+}
+
+template <typename T>
+__device__ __forceinline__ bool msda_sample_geom(T x, T y, int H, int W, int start, int (&tok)[4],
+                                                 T& lh, T& lw, bool fma = false) {
+  int h0, w0;
+  return msda_sample_geom_hw(x, y, H, W, start, tok, lh, lw, h0, w0, fma);
 }
 
 // ---- memory helpers ---------------------------------------------------------------------

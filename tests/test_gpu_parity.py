@@ -40,7 +40,7 @@ def test_extension_is_loaded_from_the_tree():
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-@pytest.mark.parametrize("path", ["auto", "tiled", "generic"])
+@pytest.mark.parametrize("path", ["auto", "tiled", "aggregate", "generic"])
 def test_golden_forward_backward(case, path):
     """auto = what the library picks (warp-per-query "split" kernels at these sizes for D=32);
     tiled = the lane-group-per-query kernels used for large problems; generic = any-shape kernels."""
@@ -49,7 +49,8 @@ def test_golden_forward_backward(case, path):
     g = load_golden(case)
     f64 = g["value"].dtype == torch.float64
     v, shp, st, loc, w, go = _to_dev(g)
-    flags = {"auto": 0, "tiled": _capi.FLAG_NO_SPLIT, "generic": _capi.FLAG_FORCE_GENERIC}[path]
+    flags = {"auto": 0, "tiled": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_AGGREGATE,
+             "aggregate": _capi.FLAG_AGGREGATE, "generic": _capi.FLAG_FORCE_GENERIC}[path]
     out = _ext().ms_deform_attn_forward(v, shp, st, loc, w, 64, _flags=flags)
     gv, gl, ga = _ext().ms_deform_attn_backward(v, shp, st, loc, w, go, 64, _flags=flags)
     ft, bt = (1e-12, 1e-11) if f64 else (FWD_TOL, BWD_TOL)
@@ -132,16 +133,20 @@ def test_gradcheck_like_reference(channels):
     assert gradcheck(MSDeformAttnFunction.apply, (value, shapes, starts, loc, w, 2))
 
 
-@pytest.mark.parametrize("kind,n,lq", [("E", 1, None), ("U", 2, 600), ("Dn", 2, 1100)])
-def test_dino_shape_against_c_oracle(kind, n, lq, c_oracle):
-    """Full DINO 4-scale R50 800x1333 pyramid (S=22223, M=8, D=32, L=4, P=4) against the C oracle."""
-    from richsem_b200 import synthetic as syn
+@pytest.mark.parametrize("kind,n,lq,bflags", [("E", 1, None, 0), ("E", 1, None, "noagg"), ("U", 2, 600, 0),
+                                              ("U", 2, 600, "agg"), ("Dn", 2, 1100, 0), ("Dn", 2, 1100, "agg")])
+def test_dino_shape_against_c_oracle(kind, n, lq, bflags, c_oracle):
+    """Full DINO 4-scale R50 800x1333 pyramid (S=22223, M=8, D=32, L=4, P=4) against the C oracle.
+    Encoder ("E") takes the pre-aggregating backward by default; "agg" forces it on inputs without
+    locality (almost every point then falls back to direct reductions), "noagg" disables it."""
+    from richsem_b200 import _capi, synthetic as syn
 
+    bflags = {0: 0, "agg": _capi.FLAG_AGGREGATE, "noagg": _capi.FLAG_NO_AGGREGATE}[bflags]
     shapes = syn.level_shapes(800, 1333)
     i = syn.make_inputs(kind, n, shapes, "cuda:0", seed=21, lq=lq)
     out = _ext().ms_deform_attn_forward(i["value"], i["shapes"], i["starts"], i["loc"], i["attw"], 64)
     gv, gl, ga = _ext().ms_deform_attn_backward(i["value"], i["shapes"], i["starts"], i["loc"], i["attw"],
-                                                i["grad_out"], 64)
+                                                i["grad_out"], 64, _flags=bflags)
     v, loc, w, go = (i[k].cpu() for k in ("value", "loc", "attw", "grad_out"))
     want = c_oracle.forward(v, shapes, loc, w)
     assert rel_err(out.cpu(), want) < FWD_TOL
@@ -163,7 +168,7 @@ def test_query_order_does_not_change_results(monkeypatch):
     from richsem_b200 import _capi
 
     args = (i["value"], i["shapes"], i["starts"], i["loc"], i["attw"])
-    nosplit = _capi.FLAG_NO_SPLIT
+    nosplit = _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_AGGREGATE
     a = _ext().ms_deform_attn_forward(*args, 64, _flags=nosplit)
     ga = _ext().ms_deform_attn_backward(*args, i["grad_out"], 64, _flags=nosplit)
     monkeypatch.setenv("MSDA_B200_QUERY_ORDER", "natural")
@@ -221,6 +226,22 @@ def test_deterministic_mode_is_bitwise_reproducible_and_close_to_atomic():
     e3 = b(*args2)
     assert torch.equal(e1[0], e2[0])
     assert rel_err(e1[0], e3[0]) < BWD_TOL
+
+
+def test_aggregated_backward_matches_plain_backward_bf16_and_five_levels():
+    """Pre-aggregating backward vs the plain atomic one: bf16 value, and a 5-level pyramid (kL=5 decodes
+    two levels in some threads)."""
+    from richsem_b200 import _capi, synthetic as syn
+
+    b = _ext().ms_deform_attn_backward
+    for shapes, dtype in (([(40, 61), (20, 31), (10, 16), (5, 8)], torch.bfloat16),
+                          ([(33, 47), (17, 24), (9, 12), (5, 6), (3, 3)], torch.float32)):
+        i = syn.make_inputs("E", 2, shapes, "cuda:0", seed=4, dtype=dtype)
+        args = (i["value"], i["shapes"], i["starts"], i["loc"], i["attw"], i["grad_out"], 64)
+        x = b(*args, _flags=_capi.FLAG_AGGREGATE | _capi.FLAG_NO_SPLIT)
+        y = b(*args, _flags=_capi.FLAG_NO_AGGREGATE | _capi.FLAG_NO_SPLIT)
+        assert rel_err(x[0], y[0]) < 1e-5
+        assert torch.equal(x[1], y[1]) and torch.equal(x[2], y[2])
 
 
 @pytest.mark.parametrize("path", ["auto", "tiled", "generic"])
