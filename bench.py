@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--workload", default="encoder6", choices=sorted(WORKLOADS))
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--aggregate", action="store_true", help="backward: pre-aggregate grad_value on chip (opt-in)")
+    ap.add_argument("--lib-flags", type=lambda x: int(x, 0), default=0,
+                    help="extra MSDA_FLAG_* bits for forward and backward (kernel-selection experiments)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -228,6 +230,7 @@ def run_b200(args):
     flags = _capi.FLAG_DETERMINISTIC if args.deterministic else 0
     if args.aggregate:
         flags |= _capi.FLAG_AGGREGATE
+    flags |= args.lib_flags
     vb = 2 if vdt == "bf16" else 4
     fwd_bytes, bwd_bytes = syn.algorithmic_bytes(bs, S, Lq, value_bytes=vb, out_bytes=vb)
     in_bytes = sum(s[k].numel() * s[k].element_size() for s in sets for k in ("value", "loc", "attw", "grad_out"))
@@ -236,7 +239,7 @@ def run_b200(args):
         for i, s in enumerate(sets):
             if timing is not None:
                 timing["f0"][i].record()
-            s["out"] = ext.ms_deform_attn_forward(s["value"], shp, st, s["loc"], s["attw"], 64)
+            s["out"] = ext.ms_deform_attn_forward(s["value"], shp, st, s["loc"], s["attw"], 64, _flags=args.lib_flags)
             if timing is not None:
                 timing["f1"][i].record()
         for i in reversed(range(layers)):

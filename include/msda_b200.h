@@ -70,6 +70,8 @@ extern "C" {
                                                  cuh:285-286, i.e. the compiled reference; default is mul-then-sub  */
 #define MSDA_FLAG_NO_AGGREGATE 0x20u           /* backward: never pre-aggregate grad_value on chip (comparison)    */
 #define MSDA_FLAG_AGGREGATE 0x40u              /* backward: pre-aggregate even without a query_order (testing)     */
+#define MSDA_FLAG_NO_WINDOW 0x80u              /* backward: keep the L1-gather tiled kernel instead of the shared-memory window kernel */
+#define MSDA_FLAG_WINDOW_FWD 0x100u            /* forward: use the shared-memory window kernel (opt-in, slower on B200)        */
 #define MSDA_FLAG_NO_SPLIT 0x8u               /* small problems: keep the lane-group-per-query kernels (testing)    */
 
 typedef void* msda_stream_t; /* cudaStream_t */

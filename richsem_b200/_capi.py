@@ -25,6 +25,8 @@ FLAG_NO_SPLIT = 0x8
 FLAG_COORDS_FMA = 0x10
 FLAG_NO_AGGREGATE = 0x20
 FLAG_AGGREGATE = 0x40
+FLAG_NO_WINDOW = 0x80
+FLAG_WINDOW_FWD = 0x100
 MAX_LEVELS = 16
 
 _vp, _i, _i64p = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)

@@ -7,10 +7,6 @@
 #include <cstring>
 
 #include "msda_host.h"
-#include "msda_d32.cuh"
-#include "msda_d32_agg.cuh"
-#include "msda_det.cuh"
-#include "msda_generic.cuh"
 
 namespace {
 thread_local char g_err[512] = "";
@@ -44,13 +40,7 @@ using msda::fail;
 
 inline uint32_t opt_flags(const msda_opts* o) { return o ? o->flags : 0u; }
 
-struct Problem {
-  MsdaDims d;
-  MsdaLevels lv;
-  const int32_t* order;
-  int order_len;
-  uint32_t flags;
-};
+using msda::Problem;
 
 // Builds the constant-memory level table.  With a host mirror this is pure host work;
 // without one it is a blocking device->host copy on `stream` (documented slow path).
@@ -121,138 +111,6 @@ bool fits_int32(const MsdaDims& d) {
   return (long long)d.spatial_size * d.num_heads * d.channels < (1ll << 31);
 }
 
-int generic_grid(const MsdaDims& d) {
-  const long long tasks = (long long)d.batch * d.num_query * d.num_heads;
-  long long blocks = (tasks + 7) / 8;
-  if (blocks > 148ll * 64) blocks = 148ll * 64;
-  return (int)(blocks < 1 ? 1 : blocks);
-}
-
-// ---- tuned D=32 dispatch (fp32 and bf16 value) -----------------------------------------------
-template <typename VT, int kL, int kM>
-int launch_fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const float* loc,
-                   const float* attw, VT* out) {
-  using Cfg = msda::D32Cfg<VT, kL * 4>;
-  const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
-  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
-  msda::msda_fwd_d32_kernel<VT, kL, 4, kM><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
-      value, loc, attw, out, pb.order, pb.order_len, pb.lv, pb.d.spatial_size, pb.d.num_heads,
-      pb.d.num_query);
-  return after_launch("msda_fwd_d32_kernel");
-}
-template <typename VT, int kL, int kM, bool kScatter>
-int launch_bwd_d32(cudaStream_t s, const Problem& pb, const VT* grad_out, const VT* value,
-                   const float* loc, const float* attw, float* gv, float* gl, float* ga) {
-  using Cfg = msda::D32Cfg<VT, kL * 4>;
-  const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
-  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
-  msda::msda_bwd_d32_kernel<VT, kL, 4, kM, kScatter><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
-      grad_out, value, loc, attw, gv, gl, ga, pb.order, pb.order_len, pb.lv, pb.d.spatial_size,
-      pb.d.num_heads, pb.d.num_query);
-  return after_launch("msda_bwd_d32_kernel");
-}
-
-template <typename VT, int kL, int kM>
-int launch_fwd_split(cudaStream_t s, const Problem& pb, const VT* value, const float* loc,
-                     const float* attw, VT* out) {
-  constexpr int QPB = msda::kSplitThreads / 32;
-  dim3 grid(((pb.d.num_query + QPB - 1) / QPB) * pb.d.num_heads, pb.d.batch);
-  msda::msda_fwd_d32_split_kernel<VT, kL, 4, kM><<<grid, msda::kSplitThreads, 0, s>>>(
-      value, loc, attw, out, pb.lv, pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
-  return after_launch("msda_fwd_d32_split_kernel");
-}
-template <typename VT, int kL, int kM, bool kScatter>
-int launch_bwd_split(cudaStream_t s, const Problem& pb, const VT* grad_out, const VT* value,
-                     const float* loc, const float* attw, float* gv, float* gl, float* ga) {
-  constexpr int QPB = msda::kSplitThreads / 32;
-  dim3 grid(((pb.d.num_query + QPB - 1) / QPB) * pb.d.num_heads, pb.d.batch);
-  msda::msda_bwd_d32_split_kernel<VT, kL, 4, kM, kScatter><<<grid, msda::kSplitThreads, 0, s>>>(
-      grad_out, value, loc, attw, gv, gl, ga, pb.lv, pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
-  return after_launch("msda_bwd_d32_split_kernel");
-}
-
-template <typename VT, int kL, int kM>
-int launch_bwd_agg(cudaStream_t s, const Problem& pb, const VT* grad_out, const VT* value,
-                   const float* loc, const float* attw, float* gv, float* gl, float* ga) {
-  using Cfg = msda::AggCfg<kL>;
-  auto kern = msda::msda_bwd_d32_agg_kernel<VT, kL, kM>;
-  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-  if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_bwd_d32_agg_kernel)");
-  const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
-  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
-  kern<<<grid, msda::kAggThreads, Cfg::SMEM_BYTES, s>>>(grad_out, value, loc, attw, gv, gl, ga, pb.order,
-                                                        pb.order_len, pb.lv, pb.d.spatial_size,
-                                                        pb.d.num_heads, pb.d.num_query);
-  return after_launch("msda_bwd_d32_agg_kernel");
-}
-
-// On-chip pre-aggregation of grad_value (msda_d32_agg.cuh) cuts the L2 reductions 8.7x but, as
-// measured on B200 (profiles/r1_bwd_agg.md), its counting sort makes it latency-bound: 0.62 ms
-// against 0.47 ms for the plain kernel at the headline shape.  It stays opt-in.
-inline bool use_aggregate(const Problem& pb) {
-  if (pb.flags & MSDA_FLAG_NO_AGGREGATE) return false;
-  return (pb.flags & MSDA_FLAG_AGGREGATE) != 0;
-}
-
-// Few (query, head) pairs (decoder cross-attention): one warp per pair instead of one lane group.
-inline bool use_split(const Problem& pb) {
-  return !(pb.flags & MSDA_FLAG_NO_SPLIT) &&
-         (long long)pb.d.batch * pb.d.num_query * pb.d.num_heads <= 65536 && pb.d.num_levels >= 2 &&
-         pb.d.num_levels <= 6;
-}
-
-#define MSDA_SWITCH_L(L_, CALL)                                                              \
-  switch (L_) {                                                                              \
-    case 1: return CALL(1);                                                                  \
-    case 2: return CALL(2);                                                                  \
-    case 3: return CALL(3);                                                                  \
-    case 4: return CALL(4);                                                                  \
-    case 5: return CALL(5);                                                                  \
-    case 6: return CALL(6);                                                                  \
-    default: return fail(MSDA_ERR_UNSUPPORTED, "no tuned kernel for num_levels=%d", L_);      \
-  }
-
-template <typename VT>
-int fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const float* loc, const float* attw,
-            VT* out) {
-  if (use_split(pb)) {
-    if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_fwd_split<VT, 4, 8>(s, pb, value, loc, attw, out);
-#define CALL(L) launch_fwd_split<VT, L, 0>(s, pb, value, loc, attw, out)
-    MSDA_SWITCH_L(pb.d.num_levels, CALL)
-#undef CALL
-  }
-  // the DINO / RichSem configuration (8 heads, 4 or 5 levels) gets the head count baked in
-  if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_fwd_d32<VT, 4, 8>(s, pb, value, loc, attw, out);
-  if (pb.d.num_heads == 8 && pb.d.num_levels == 5) return launch_fwd_d32<VT, 5, 8>(s, pb, value, loc, attw, out);
-#define CALL(L) launch_fwd_d32<VT, L, 0>(s, pb, value, loc, attw, out)
-  MSDA_SWITCH_L(pb.d.num_levels, CALL)
-#undef CALL
-}
-template <typename VT, bool kScatter>
-int bwd_d32(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
-            const float* attw, float* gv, float* gl, float* ga) {
-  if (kScatter && use_aggregate(pb) && (!use_split(pb) || (pb.flags & MSDA_FLAG_AGGREGATE))) {
-    if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_bwd_agg<VT, 4, 8>(s, pb, go, value, loc, attw, gv, gl, ga);
-#define CALL(L) launch_bwd_agg<VT, L, 0>(s, pb, go, value, loc, attw, gv, gl, ga)
-    MSDA_SWITCH_L(pb.d.num_levels, CALL)
-#undef CALL
-  }
-  if (use_split(pb)) {
-    if (pb.d.num_heads == 8 && pb.d.num_levels == 4)
-      return launch_bwd_split<VT, 4, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
-#define CALL(L) launch_bwd_split<VT, L, 0, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
-    MSDA_SWITCH_L(pb.d.num_levels, CALL)
-#undef CALL
-  }
-  if (pb.d.num_heads == 8 && pb.d.num_levels == 4)
-    return launch_bwd_d32<VT, 4, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
-  if (pb.d.num_heads == 8 && pb.d.num_levels == 5)
-    return launch_bwd_d32<VT, 5, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
-#define CALL(L) launch_bwd_d32<VT, L, 0, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
-  MSDA_SWITCH_L(pb.d.num_levels, CALL)
-#undef CALL
-}
-
 // ---- templated front ends --------------------------------------------------------------------
 // TV: storage type of value / out / grad_out;  TA: type of locations, weights and all gradients.
 template <typename TV, typename TA>
@@ -268,11 +126,16 @@ int forward_impl(cudaStream_t s, const TV* value, const int64_t* shapes, const i
   if (batch == 0 || num_query == 0) return MSDA_OK;
   if constexpr (sizeof(TA) == 4) {
     if (!(pb.flags & MSDA_FLAG_FORCE_GENERIC) && fast_shape(sizeof(TV), channels, num_levels, num_point) &&
-        fits_int32(pb.d) && aligned(value, 16) && aligned(loc, 8) && aligned(out, 16))
-      return fwd_d32<TV>(s, pb, value, loc, attw, out);
+        fits_int32(pb.d) && aligned(value, 16) && aligned(loc, 16) && aligned(attw, 16) && aligned(out, 16))
+    {
+      // measured on B200 (profiles/): the shared-memory window forward is latency-bound behind its front end
+      // (0.18 ms per bs=2 encoder layer against 0.14 ms for the L1-gather kernel), so it is opt-in; the window
+      // backward is the default for large problems (0.41 ms against 0.47 ms)
+      const bool window = !msda::use_split(pb) && (pb.flags & MSDA_FLAG_WINDOW_FWD) && !(pb.flags & MSDA_FLAG_NO_WINDOW);
+      return window ? msda::fwd_d32_win<TV>(s, pb, value, loc, attw, out) : msda::fwd_d32<TV>(s, pb, value, loc, attw, out);
+    }
   }
-  msda::msda_fwd_generic_kernel<TV, TA><<<generic_grid(pb.d), 256, 0, s>>>(value, loc, attw, out, pb.lv, pb.d);
-  return after_launch("msda_fwd_generic_kernel");
+  return msda::fwd_generic<TV, TA>(s, pb, value, loc, attw, out);
 }
 
 template <typename TV, typename TA>
@@ -303,24 +166,21 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
                       aligned(value, 16) && aligned(gv, 16) && aligned(loc, 16) && aligned(attw, 16) &&
                       aligned(grad_out, 16) && aligned(gl, 8);
     if (fast) {
-      rc = det ? bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
-               : bwd_d32<TV, true>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
+      const bool window = !det && !msda::use_split(pb) && !(pb.flags & (MSDA_FLAG_NO_WINDOW | MSDA_FLAG_AGGREGATE));
+      rc = window ? msda::bwd_d32_win<TV>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
+           : det  ? msda::bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
+                  : msda::bwd_d32<TV, true>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
       if (rc != MSDA_OK || !det) return rc;
     }
     if (det) {
       if (!fast) {
-        msda::msda_bwd_generic_kernel<TV, TA, false><<<generic_grid(pb.d), 256, 0, s>>>(
-            grad_out, value, loc, attw, gv, gl, ga, pb.lv, pb.d);
-        if ((rc = after_launch("msda_bwd_generic_kernel<noscatter>"))) return rc;
+        if ((rc = msda::bwd_generic<TV, TA>(s, pb, false, grad_out, value, loc, attw, gv, gl, ga))) return rc;
       }
-      return msda::deterministic_grad_value<TV>(s, pb.d, pb.lv, grad_out, loc, attw, gv,
-                                                opts ? opts->workspace : nullptr,
-                                                opts ? opts->workspace_bytes : 0);
+      return msda::det_grad_value<TV>(s, pb, grad_out, loc, attw, gv, opts ? opts->workspace : nullptr,
+                                      opts ? opts->workspace_bytes : 0);
     }
   }
-  msda::msda_bwd_generic_kernel<TV, TA, true><<<generic_grid(pb.d), 256, 0, s>>>(grad_out, value, loc, attw, gv,
-                                                                              gl, ga, pb.lv, pb.d);
-  return after_launch("msda_bwd_generic_kernel");
+  return msda::bwd_generic<TV, TA>(s, pb, true, grad_out, value, loc, attw, gv, gl, ga);
 }
 
 }  // namespace
@@ -409,16 +269,12 @@ int msda_debug_corners_f32(msda_stream_t stream, const int64_t* spatial_shapes,
   lv.coord_fma = (opt_flags(opts) & MSDA_FLAG_COORDS_FMA) ? 1 : 0;
   const long long n = (long long)batch * num_query * num_heads * num_levels * num_point;
   if (n == 0) return MSDA_OK;
-  long long blocks = (n + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  msda::msda_corners_kernel<<<(int)blocks, 256, 0, s>>>(sampling_loc, corners, lv, n, num_levels, num_point);
-  return after_launch("msda_corners_kernel");
+  return msda::corners_probe(s, lv, sampling_loc, corners, n, num_levels, num_point);
 }
 
 size_t msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels,
                                      int num_levels, int num_query, int num_point) {
-  return msda::deterministic_workspace_bytes(batch, spatial_size, num_heads, channels, num_levels,
-                                             num_query, num_point);
+  return msda::det_workspace_bytes(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point);
 }
 
 int msda_has_fast_path(int dtype_bytes, int channels, int num_levels, int num_point) {

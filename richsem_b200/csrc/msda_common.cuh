@@ -82,6 +82,18 @@ __device__ __forceinline__ bool msda_sample_geom(T x, T y, int H, int W, int sta
   return msda_sample_geom_hw(x, y, H, W, start, tok, lh, lw, h0, w0, fma);
 }
 
+// ---- packed fp32 math (Blackwell FFMA2: two fp32 FMAs per issued instruction) --------------
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
 // ---- memory helpers ---------------------------------------------------------------------
 // Streaming operands (sampling_loc, attn_weight, grad_out, outputs) are touched once:
 // keep them out of L1 so the gathered `value` rows own it.

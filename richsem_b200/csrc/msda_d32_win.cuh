@@ -1,0 +1,825 @@
+// msda_d32_win.cuh — "window" kernels for head_dim 32: the value rows a block of queries samples
+// are staged ONCE in shared memory; the forward gathers from there, the backward walks the block's
+// samples sorted by window cell so that value rows AND grad_value partial sums live in registers.
+//
+// Why (measured on B200, scratch/gather_bw.cu, scratch/tma_stage.cu, scratch/smem_atomics.cu):
+//   * a gather of 128-byte rows out of L1 (LDG.128, 4 rows per warp instruction, all hits) runs at
+//     1.9 SM-cycles per row — the rate the tiled kernels (msda_d32.cuh) sit on — while the same gather
+//     out of shared memory (LDS.128) runs at 1.04 cycles per row, the 128 B/clk limit of the data pipe;
+//   * L2 retires scattered fp32 row reductions at 5.8 SM-cycles per row per SM (6.4 TB/s chip-wide):
+//     22.75 M of them per bs=2 encoder layer is the 455 us floor of the plain backward; shared-memory
+//     float atomics are a CAS loop (14.7 cycles per row; 5.1 with a 128-bit CAS), so merging must be
+//     "owner computes", and native int ATOMS.ADD (0.1 cycles per lane) makes a counting sort cheap;
+//   * encoder self-attention is spatially local: the 64 queries of an 8x8-pixel patch put their
+//     64*L*P*4 = 4096 corner reads per head on ~330 distinct rows (scratch/bbox_stats.py).
+//
+// Block = one head x a tile of 64 queries (host-provided patch order for encoder self-attention).
+//   front end  thread (level, query) decodes 4 sampling points (bit-exact geometry of msda_common.cuh);
+//              REDUX + shared atomics give each level's bounding box of (h0, w0).  Levels whose box
+//              [hmin, hmax+1] x [wmin, wmax+1] fits what is left of the row pool get a window (coarsest
+//              level first: smallest boxes); warps copy whole window lines with 16-byte cp.async,
+//              zero-filling rows outside the image, so windowed samples need no corner predicates.
+//              Levels that do not fit stay "direct": their samples gather from global memory.
+//   forward    lane groups (8 lanes x float4 for fp32 rows, 4 lanes x 8 bf16) walk the records of their
+//              queries: one broadcast LDS.128 per point, four row reads, 16 FFMA.
+//   backward   the windowed samples are counting-sorted by cell (= pool row of corner (h0,w0)); each lane
+//              group walks a contiguous chunk of the sorted list holding the current cell's four value
+//              rows and four grad_value accumulators in registers: per sample one LDS.128 of grad_out,
+//              16 FFMA of dot products, 16 FFMA of accumulation; a cell change flushes two (adjacent
+//              cell: the other two slide over) or four accumulators with REDG.ADD.F32x4 — ~5x fewer
+//              L2 reductions than one per corner.  grad_sampling_loc / grad_attn_weight are parked in the
+//              record slots and written out coalesced at the end.
+//
+// The arithmetic restates models/richsem/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299 (forward),
+// :87-159 (gradients); nothing of that file's thread mapping or reductions is used.
+#pragma once
+
+#include <climits>
+
+#include "msda_d32.cuh"
+
+namespace msda {
+
+constexpr int kWinThreads = 256;
+// Rows of the window pool.  Forward: 448 rows = 75 KB per block with the records, three blocks per SM.
+// Backward: 448 rows = 89 KB with the sort structures, two blocks per SM (128 registers per thread);
+// measured per bs=2 encoder layer: 256 rows 0.464 ms, 320 0.442, 384 0.425, 448 0.414, 592 0.434.
+#ifndef MSDA_WIN_POOL_FWD
+#define MSDA_WIN_POOL_FWD 448
+#endif
+#ifndef MSDA_WIN_POOL_BWD
+#define MSDA_WIN_POOL_BWD 448
+#endif
+constexpr int kWinPoolFwd = MSDA_WIN_POOL_FWD;
+constexpr int kWinPoolBwd = MSDA_WIN_POOL_BWD;
+
+#ifdef MSDA_WIN_TIMING
+// Phase timing (debug builds only): per-phase SM-clock sums over all blocks, read by msda_debug_win_timing().
+__device__ unsigned long long g_win_timing[16];
+#define WIN_T(k, t0)                                                                          \
+  do {                                                                                        \
+    if (threadIdx.x == 0) {                                                                   \
+      const long long now_ = clock64();                                                       \
+      atomicAdd(&g_win_timing[k], (unsigned long long)(now_ - (t0)));                         \
+      (t0) = now_;                                                                            \
+    }                                                                                         \
+  } while (0)
+#else
+#define WIN_T(k, t0) do { } while (0)
+#endif
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// 16-byte global->shared copy that bypasses L1 and registers; src_bytes = 0 writes zeros.
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// Pulls the line holding p into L2 (no register, no L1): used one wave of blocks ahead of the demand load.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// How many tiles ahead a block prefetches sampling locations / weights / grad_out (~ one wave of blocks:
+// 148 SMs x 2..3 blocks / 8 heads).
+constexpr int kWinPrefetchTiles = 48;
+
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// Shared-memory row reads of the window (VT rows of 32 channels).
+template <typename VT>
+struct WinRow;
+template <>
+struct WinRow<float> {
+  static constexpr int ROWB = 128;
+  static __device__ __forceinline__ void lds(const unsigned char* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <>
+struct WinRow<__nv_bfloat16> {
+  static constexpr int ROWB = 64;
+  static __device__ __forceinline__ void lds(const unsigned char* p, float (&v)[8]) {
+    RowTraits<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(p), v);
+  }
+};
+
+template <typename VT, int kL, int kWinPool>
+struct WinCfg {
+  static constexpr int LP = kL * 4;
+  static constexpr int NLV = (kL + 3) / 4;            // levels decoded per thread
+  static constexpr int REC_STRIDE = LP + 1;           // float4 per query (+1: bank skew)
+  static constexpr int ROWB = WinRow<VT>::ROWB;
+  static constexpr int POOL_BYTES = (kWinPool + 2) * ROWB;  // + two all-zero rows for skipped samples
+  static constexpr int REC_BYTES = kTileQ * REC_STRIDE * 16;
+  static constexpr int BB_BYTES = 32 * 4;
+  static constexpr int FWD_SMEM = POOL_BYTES + REC_BYTES + BB_BYTES;
+  // backward extras
+  static constexpr int HIST_N = ((kWinPool + kWinThreads - 1) / kWinThreads) * kWinThreads;  // padded for the scan
+  static constexpr int SPT = HIST_N / kWinThreads;
+  static constexpr int GO_BYTES = kTileQ * 32 * 4;            // grad_out rows of the tile, fp32
+  static constexpr int HIST_BYTES = (HIST_N + 4) * 4;         // counts -> offsets (+ total)
+  static constexpr int ROWOFF_BYTES = (kWinPool + 2) * 4;
+  static constexpr int SORTED_BYTES = ((kTileQ * LP * 2 + 15) / 16) * 16 + 16;
+  static constexpr int OFF_GO = POOL_BYTES + REC_BYTES + BB_BYTES;
+  static constexpr int OFF_HIST = OFF_GO + GO_BYTES;
+  static constexpr int OFF_ROWOFF = OFF_HIST + HIST_BYTES;
+  static constexpr int OFF_SORTED = OFF_ROWOFF + ROWOFF_BYTES;
+  static constexpr int BWD_SMEM = OFF_SORTED + SORTED_BYTES + 128;
+  static_assert(kL <= 8, "per-level state is kept in 8-entry arrays");
+  static_assert(kWinPool + 2 < 32768, "two pool rows are packed in one record word");
+  static_assert(kTileQ * LP < 65536, "sample ids are stored as 16-bit");
+};
+
+// Per-level window decision, computed identically by every thread from the block's bounding boxes.
+template <int kL>
+struct WinAlloc {
+  int base[kL];        // first pool row of the level's window, -1: level is gathered from global memory
+  int bw[kL], bh[kL];  // window size in rows
+  int hm[kL], wm[kL];  // window origin (pixel coordinates, may be -1)
+};
+
+template <int kL, int kWinPool>
+__device__ __forceinline__ void win_allocate(const int* bb, WinAlloc<kL>& wa) {
+  // bb: [0,8) hmin  [8,16) hmax  [16,24) wmin  [24,32) wmax
+  int used = 0;
+#pragma unroll
+  for (int l = kL - 1; l >= 0; --l) {
+    const int hm = bb[l], hM = bb[8 + l], wm = bb[16 + l], wM = bb[24 + l];
+    wa.base[l] = -1;
+    wa.bw[l] = 2; wa.bh[l] = 2; wa.hm[l] = 0; wa.wm[l] = 0;
+    if (hm <= hM) {
+      const unsigned bh = (unsigned)(hM - hm) + 2u, bw = (unsigned)(wM - wm) + 2u;
+      if (bh <= (unsigned)kWinPool && bw <= (unsigned)kWinPool && used + (int)(bh * bw) <= kWinPool) {
+        wa.base[l] = used;
+        wa.bw[l] = (int)bw; wa.bh[l] = (int)bh; wa.hm[l] = hm; wa.wm[l] = wm;
+        used += (int)(bh * bw);
+      }
+    }
+  }
+}
+
+// Stages the windows of all allocated levels: warp w copies window lines w, w+8, ... of each level.
+// rowoff (backward only): per pool row, the element offset of the row inside the image's value block,
+// or -1 for rows outside the image.
+template <typename VT, int kL, bool kRowOff>
+__device__ __forceinline__ void win_stage(const WinAlloc<kL>& wa, const MsdaLevels& lv, const VT* value_img,
+                                          const int m, const int M, unsigned char* pool, int* rowoff) {
+  constexpr int ROWB = WinRow<VT>::ROWB, G = ROWB / 16, EPL = 16 / (int)sizeof(VT);  // elements per 16 B
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rw0 = lane / G, jj = lane % G;
+  const unsigned pool_s = smem_u32(pool);
+#pragma unroll
+  for (int l = kL - 1; l >= 0; --l) {
+    if (wa.base[l] < 0) continue;
+    const int bw = wa.bw[l], H = lv.H[l], W = lv.W[l];
+    for (int rh = warp; rh < wa.bh[l]; rh += kWinThreads / 32) {
+      const int h = wa.hm[l] + rh;
+      const bool hin = (unsigned)h < (unsigned)H;
+      const int row_l = wa.base[l] + rh * bw;                            // pool row of the line's first row
+      const int off_l = ((lv.start[l] + h * W + wa.wm[l]) * M + m) * 32;  // its element offset (virtual if outside)
+      for (int rw = rw0; rw < bw; rw += 32 / G) {
+        const bool inb = hin && (unsigned)(wa.wm[l] + rw) < (unsigned)W;
+        const int off = off_l + rw * (M * 32);
+        cp_async16(pool_s + (unsigned)((row_l + rw) * ROWB + jj * 16), value_img + (inb ? off : 0) + jj * EPL,
+                   inb ? 16 : 0);
+        if (kRowOff && jj == 0) rowoff[row_l + rw] = inb ? off : -1;
+      }
+    }
+  }
+}
+
+// One decoded sampling point held in registers between the phases.
+struct WinPoint {
+  int h0, w0;
+  float lh, lw, a;
+  bool in;
+};
+
+// Record word of a point.
+//   level served from the window: pool row of corner (h0,w0) | pool row of corner (h1,w0) << 16; the
+//     (.,w1) corners are the next rows.  A skipped sample points at the pool's two all-zero rows (and
+//     carries weight 0), so the gather loop needs no branch.
+//   level gathered from global memory: element offset of corner (h0,w0)'s row | 4-bit corner mask
+//     (as msda_d32.cuh); skipped -> 0.
+template <int kWinPool>
+__device__ __forceinline__ int win_record_code(const WinPoint& pt, const int base, const int bw, const int hm,
+                                               const int wm, const int H, const int W, const int start,
+                                               const int m, const int M) {
+  if (base >= 0) {
+    if (!pt.in) return kWinPool | (kWinPool << 16);
+    const int row0 = base + (pt.h0 - hm) * bw + (pt.w0 - wm);
+    return row0 | ((row0 + bw) << 16);
+  }
+  if (!pt.in) return 0;
+  const bool h0ok = pt.h0 >= 0, w0ok = pt.w0 >= 0, h1ok = pt.h0 + 1 <= H - 1, w1ok = pt.w0 + 1 <= W - 1;
+  const int mask = (h0ok && w0ok) | ((h0ok && w1ok) << 1) | ((h1ok && w0ok) << 2) | ((h1ok && w1ok) << 3);
+  return mask ? (((start + pt.h0 * W + pt.w0) * M + m) * 32) | mask : 0;
+}
+
+// Decodes the 4 points of level l of (query, head) qm and folds them into the thread's bounding box.
+__device__ __forceinline__ void win_decode_level(const float* __restrict__ loc, const float* __restrict__ attw,
+                                                 const size_t qm, const int LP, const int l, const MsdaLevels& lv,
+                                                 WinPoint (&pt)[4], int& hmn, int& hmx, int& wmn, int& wmx) {
+  const float* lp = loc + (qm * LP + l * 4) * 2;
+  const float4 xy01 = ld_stream_f4(lp), xy23 = ld_stream_f4(lp + 4);
+  const float4 aw = ld_stream_f4(attw + qm * LP + l * 4);
+  const int H = lv.H[l], W = lv.W[l];
+  const bool fma = lv.coord_fma != 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float x = i == 0 ? xy01.x : i == 1 ? xy01.z : i == 2 ? xy23.x : xy23.z;
+    const float y = i == 0 ? xy01.y : i == 1 ? xy01.w : i == 2 ? xy23.y : xy23.w;
+    pt[i].a = i == 0 ? aw.x : i == 1 ? aw.y : i == 2 ? aw.z : aw.w;
+    int tok[4];
+    pt[i].in = msda_sample_geom_hw(x, y, H, W, 0, tok, pt[i].lh, pt[i].lw, pt[i].h0, pt[i].w0, fma);
+    if (pt[i].in) {
+      hmn = min(hmn, pt[i].h0); hmx = max(hmx, pt[i].h0);
+      wmn = min(wmn, pt[i].w0); wmx = max(wmx, pt[i].w0);
+    }
+  }
+}
+
+// Front end shared by the forward and backward window kernels: decode, bounding boxes, window
+// allocation, staging (cp.async left in flight), records.  Thread t decodes level (t / 64) [+4] of
+// query t % 64, so the level is warp-uniform.  kBwd additionally fills rowoff and counts the windowed
+// samples per cell (hist; rank[][] = the sample's arrival order inside its cell).
+template <typename VT, int kL, int kWinPool, bool kBwd>
+__device__ __forceinline__ void win_front_end(const VT* __restrict__ value_img, const float* __restrict__ loc,
+                                              const float* __restrict__ attw, const int q, const size_t qm,
+                                              const int qpf, const size_t qm_pf,
+                                              const int m, const int M, const MsdaLevels& lv,
+                                              unsigned char* pool, float4* rec, int* bb, int* rowoff, int* hist,
+                                              WinAlloc<kL>& wa, WinPoint (&pts)[WinCfg<VT, kL, kWinPool>::NLV][4],
+                                              int (&rank)[WinCfg<VT, kL, kWinPool>::NLV][4], long long& tph) {
+  using Cfg = WinCfg<VT, kL, kWinPool>;
+  const int t = threadIdx.x, lane = t & 31;
+  const int ql = t & (kTileQ - 1), slot = t / kTileQ;
+  if (t < 32) bb[t] = (t & 8) ? INT_MIN : INT_MAX;  // [0,8) hmin [8,16) hmax [16,24) wmin [24,32) wmax
+  if (t >= 32 && t < 32 + 2 * Cfg::ROWB / 16)
+    reinterpret_cast<uint4*>(pool + kWinPool * Cfg::ROWB)[t - 32] = make_uint4(0u, 0u, 0u, 0u);
+  if (kBwd) {
+#pragma unroll
+    for (int k = 0; k < Cfg::SPT; ++k) hist[t + k * kWinThreads] = 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int li = 0; li < Cfg::NLV; ++li) {
+    const int l = slot + 4 * li;  // warp-uniform
+    int hmn = INT_MAX, hmx = INT_MIN, wmn = INT_MAX, wmx = INT_MIN;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pts[li][i] = WinPoint{0, 0, 0.f, 0.f, 0.f, false};
+    if (l < kL) {
+      if (q >= 0) win_decode_level(loc, attw, qm, Cfg::LP, l, lv, pts[li], hmn, hmx, wmn, wmx);
+      if (qpf >= 0) {  // a later block's inputs: HBM -> L2 now, so that its decode sees L2 latency
+        prefetch_l2(loc + (qm_pf * Cfg::LP + l * 4) * 2);
+        prefetch_l2(attw + qm_pf * Cfg::LP + l * 4);
+      }
+      hmn = __reduce_min_sync(0xffffffffu, hmn); hmx = __reduce_max_sync(0xffffffffu, hmx);
+      wmn = __reduce_min_sync(0xffffffffu, wmn); wmx = __reduce_max_sync(0xffffffffu, wmx);
+      if (lane == 0 && hmn <= hmx) {
+        atomicMin(&bb[l], hmn); atomicMax(&bb[8 + l], hmx);
+        atomicMin(&bb[16 + l], wmn); atomicMax(&bb[24 + l], wmx);
+      }
+    }
+  }
+  __syncthreads();
+  WIN_T(kBwd ? 8 : 0, tph);  // decode + bounding boxes
+  win_allocate<kL, kWinPool>(bb, wa);
+  win_stage<VT, kL, kBwd>(wa, lv, value_img, m, M, pool, rowoff);
+#pragma unroll
+  for (int li = 0; li < Cfg::NLV; ++li) {
+    const int l = slot + 4 * li;
+    if (l < kL) {
+      int base = -1, bw = 0, hm = 0, wm = 0;
+#pragma unroll
+      for (int ll = 0; ll < kL; ++ll)
+        if (ll == l) { base = wa.base[ll]; bw = wa.bw[ll]; hm = wa.hm[ll]; wm = wa.wm[ll]; }
+      const int H = lv.H[l], W = lv.W[l], st = lv.start[l];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int code = win_record_code<kWinPool>(pts[li][i], base, bw, hm, wm, H, W, st, m, M);
+        rank[li][i] = -1;
+        if (kBwd && base >= 0 && pts[li][i].in) rank[li][i] = atomicAdd(&hist[code & 0xffff], 1);
+        rec[ql * Cfg::REC_STRIDE + l * 4 + i] =
+            make_float4(__int_as_float(code), pts[li][i].lh, pts[li][i].lw, pts[li][i].in ? pts[li][i].a : 0.f);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+#ifndef MSDA_WIN_FWD_MINBLOCKS
+#define MSDA_WIN_FWD_MINBLOCKS 2
+#endif
+template <typename VT, int kL, int kM>
+__global__ void __launch_bounds__(kWinThreads, MSDA_WIN_FWD_MINBLOCKS)
+msda_fwd_d32_win_kernel(const VT* __restrict__ value, const float* __restrict__ loc,
+                        const float* __restrict__ attw, VT* __restrict__ out,
+                        const int* __restrict__ order, const int order_len,
+                        const __grid_constant__ MsdaLevels lv, const int S, const int M_rt, const int Lq) {
+  constexpr int kWinPool = kWinPoolFwd;
+  using Cfg = WinCfg<VT, kL, kWinPool>;
+  using RT = RowTraits<VT>;
+  using WR = WinRow<VT>;
+  constexpr int LP = Cfg::LP, G = RT::G, C = RT::C, GPW = 32 / G, ROWB = Cfg::ROWB;
+  constexpr int QPP = (kWinThreads / 32) * GPW, PASSES = kTileQ / QPP;
+  static_assert(kTileQ * 4 == kWinThreads, "decode maps 4 threads to a query");
+
+  extern __shared__ __align__(128) unsigned char smraw[];
+  unsigned char* pool = smraw;
+  float4* rec = reinterpret_cast<float4*>(smraw + Cfg::POOL_BYTES);
+  int* bb = reinterpret_cast<int*>(smraw + Cfg::POOL_BYTES + Cfg::REC_BYTES);
+
+  const int M = kM ? kM : M_rt;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int m = blockIdx.x % M, tile = blockIdx.x / M, b = blockIdx.y;
+  const int M32 = M * 32;
+  const VT* value_img = value + (size_t)b * S * M32;
+
+  // ---- front end: decode, windows, records ---------------------------------------------------
+  long long tphase = clock64();
+  (void)tphase;
+  WinAlloc<kL> wa;
+  {
+    int q = -1;
+    const int oslot = tile * kTileQ + (t & (kTileQ - 1));
+    if (oslot < order_len) q = order ? order[oslot] : oslot;
+    const size_t qm = ((size_t)b * Lq + (q >= 0 ? q : 0)) * M + m;
+    int qpf = -1;
+    const int pslot = oslot + kWinPrefetchTiles * kTileQ;
+    if (pslot < order_len) qpf = order ? order[pslot] : pslot;
+    const size_t qm_pf = ((size_t)b * Lq + (qpf >= 0 ? qpf : 0)) * M + m;
+    WinPoint pts[Cfg::NLV][4];
+    int rank[Cfg::NLV][4];
+    win_front_end<VT, kL, kWinPool, false>(value_img, loc, attw, q, qm, qpf, qm_pf, m, M, lv, pool, rec, bb, nullptr, nullptr, wa, pts, rank, tphase);
+  }
+  WIN_T(1, tphase);  // allocation, staging issue, records
+  cp_async_wait_all();
+  __syncthreads();
+  WIN_T(2, tphase);  // wait for the windows
+
+  // ---- gather --------------------------------------------------------------------------------
+  const int g = lane / G, j = lane % G;
+  const unsigned char* pool_j = pool + j * 16;
+  const VT* value_j = value_img + j * C;
+  bool all_win = true;
+#pragma unroll
+  for (int l = 0; l < kL; ++l) all_win = all_win && wa.base[l] >= 0;
+#pragma unroll 1
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const int ql = pass * QPP + warp * GPW + g;
+    const int oslot = tile * kTileQ + ql;
+    int q = -1;
+    if (oslot < order_len) q = order ? order[oslot] : oslot;
+    if (q < 0) continue;
+    const size_t qm = ((size_t)b * Lq + q) * M + m;
+    const float4* rq = rec + ql * Cfg::REC_STRIDE;
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    // one sampling point served from the window: no predicates, no branches
+    auto from_window = [&](const float4 r) {
+      const int code = __float_as_int(r.x);
+      const float lh = r.y, lw = r.z, a = r.w;
+      const float a_hh = a * (1.f - lh), a_lh = a * lh, hw = 1.f - lw;
+      const unsigned char* p0 = pool_j + (code & 0xffff) * ROWB;
+      const unsigned char* p2 = pool_j + (code >> 16) * ROWB;
+      float v00[C], v01[C], v10[C], v11[C];
+      WR::lds(p0, v00); WR::lds(p0 + ROWB, v01); WR::lds(p2, v10); WR::lds(p2 + ROWB, v11);
+      const float w00 = a_hh * hw, w01 = a_hh * lw, w10 = a_lh * hw, w11 = a_lh * lw;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        acc[c] = fmaf(w11, v11[c], fmaf(w10, v10[c], fmaf(w01, v01[c], fmaf(w00, v00[c], acc[c]))));
+    };
+    if (all_win) {
+#pragma unroll
+      for (int p = 0; p < LP; ++p) from_window(rq[p]);
+    } else {
+#pragma unroll
+      for (int p = 0; p < LP; ++p) {
+        const int l = p / 4;
+        const float4 r = rq[p];
+        if (wa.base[l] >= 0) {  // block-uniform
+          from_window(r);
+        } else {
+          const int code = __float_as_int(r.x);
+          const float lh = r.y, lw = r.z, a = r.w;
+          const float a_hh = a * (1.f - lh), a_lh = a * lh, hw = 1.f - lw;
+          const VT* p0 = value_j + (ptrdiff_t)(code & ~31);
+          const VT* p2 = p0 + (ptrdiff_t)(lv.W[l] * M32);
+          float v[C];
+          if (code & 1) {
+            RT::load(p0, v);
+            const float w = a_hh * hw;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
+          }
+          if (code & 2) {
+            RT::load(p0 + M32, v);
+            const float w = a_hh * lw;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
+          }
+          if (code & 4) {
+            RT::load(p2, v);
+            const float w = a_lh * hw;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
+          }
+          if (code & 8) {
+            RT::load(p2 + M32, v);
+            const float w = a_lh * lw;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
+          }
+        }
+      }
+    }
+    RT::store_stream(out + qm * 32 + j * C, acc);
+  }
+#ifdef MSDA_WIN_TIMING
+  __syncthreads();
+  if (threadIdx.x == 0 && !all_win) { atomicAdd(&g_win_timing[4], (unsigned long long)(clock64() - tphase)); atomicAdd(&g_win_timing[5], 1ull); }
+  WIN_T(3, tphase);  // gather
+  if (threadIdx.x == 0) atomicAdd(&g_win_timing[7], 1ull);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+// How the 4 lanes of a sorted-pass group cover the 32 channels of a row: lane sj owns two float4 chunks
+// (chunk = 4 channels) of every fp32 row (grad_out, grad_value) and the same channels of the value rows.
+//   fp32 value: chunks sj and sj + 4; odd groups take them in the opposite order so that the two groups
+//               of a quarter-warp hit different bank halves (conflict-free LDS.128).
+//   bf16 value: one 16-byte read = channels 8 sj .. 8 sj + 7 = chunks 2 sj, 2 sj + 1.
+template <typename VT>
+struct SortLane;
+template <>
+struct SortLane<float> {
+  static __device__ __forceinline__ int chunk_a(int sg, int sj) { return sj + ((sg & 1) ? 4 : 0); }
+  static __device__ __forceinline__ int chunk_b(int sg, int sj) { return sj + ((sg & 1) ? 0 : 4); }
+  static __device__ __forceinline__ int pool_offset(int sg, int sj) { return chunk_a(sg, sj) * 16; }
+  static __device__ __forceinline__ void lds(const unsigned char* p, float (&v)[8]) {
+    const float4 lo = *reinterpret_cast<const float4*>(p);
+    const float4 hi = *reinterpret_cast<const float4*>(reinterpret_cast<uintptr_t>(p) ^ 64);  // the other half of the row
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+  }
+};
+template <>
+struct SortLane<__nv_bfloat16> {
+  static __device__ __forceinline__ int chunk_a(int, int sj) { return 2 * sj; }
+  static __device__ __forceinline__ int chunk_b(int, int sj) { return 2 * sj + 1; }
+  static __device__ __forceinline__ int pool_offset(int, int sj) { return sj * 16; }
+  static __device__ __forceinline__ void lds(const unsigned char* p, float (&v)[8]) {
+    RowTraits<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(p), v);
+  }
+};
+
+// Reduction of `C` floats held by each of the G lanes of a group into grad_value row `off`.
+template <int C>
+__device__ __forceinline__ void win_red_row(float* gvalue_j, const int off, const float (&a)[C]) {
+  if (off >= 0) {
+#pragma unroll
+    for (int c = 0; c < C; c += 4) red_add_f4(gvalue_j + off + c, a[c], a[c + 1], a[c + 2], a[c + 3]);
+  }
+}
+
+#ifndef MSDA_WIN_BWD_MINBLOCKS
+#define MSDA_WIN_BWD_MINBLOCKS 2
+#endif
+template <typename VT, int kL, int kM>
+__global__ void __launch_bounds__(kWinThreads, MSDA_WIN_BWD_MINBLOCKS)
+msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
+                        const float* __restrict__ loc, const float* __restrict__ attw,
+                        float* __restrict__ grad_value, float* __restrict__ grad_loc,
+                        float* __restrict__ grad_attw, const int* __restrict__ order,
+                        const int order_len, const __grid_constant__ MsdaLevels lv, const int S,
+                        const int M_rt, const int Lq) {
+  constexpr int kWinPool = kWinPoolBwd;
+  using Cfg = WinCfg<VT, kL, kWinPool>;
+  using RT = RowTraits<VT>;
+  using WR = WinRow<VT>;
+  constexpr int LP = Cfg::LP, G = RT::G, C = RT::C, GPW = 32 / G, ROWB = Cfg::ROWB;
+  constexpr int NG = (kWinThreads / 32) * GPW;  // lane groups per block
+  static_assert(kTileQ * 4 == kWinThreads, "decode maps 4 threads to a query");
+
+  extern __shared__ __align__(128) unsigned char smraw[];
+  unsigned char* pool = smraw;
+  float4* rec = reinterpret_cast<float4*>(smraw + Cfg::POOL_BYTES);
+  int* bb = reinterpret_cast<int*>(smraw + Cfg::POOL_BYTES + Cfg::REC_BYTES);
+  float* go_s = reinterpret_cast<float*>(smraw + Cfg::OFF_GO);
+  int* hist = reinterpret_cast<int*>(smraw + Cfg::OFF_HIST);       // counts, then exclusive offsets
+  int* rowoff = reinterpret_cast<int*>(smraw + Cfg::OFF_ROWOFF);
+  unsigned short* sorted = reinterpret_cast<unsigned short*>(smraw + Cfg::OFF_SORTED);
+  int* misc = reinterpret_cast<int*>(smraw + Cfg::OFF_SORTED + Cfg::SORTED_BYTES);  // [0,8) warp totals [8] total
+  float* lvf = reinterpret_cast<float*>(misc + 16);  // [0,8) (float)W_l  [8,16) (float)H_l
+
+  const int M = kM ? kM : M_rt;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int m = blockIdx.x % M, tile = blockIdx.x / M, b = blockIdx.y;
+  const int M32 = M * 32;
+  const size_t img = (size_t)b * S * M32;
+  const VT* value_img = value + img;
+
+  // ---- front end -------------------------------------------------------------------------------
+  long long tphase = clock64();
+  (void)tphase;
+  const int dql = t & (kTileQ - 1), dslot = t / kTileQ;
+  int dq = -1;
+  {
+    const int oslot = tile * kTileQ + dql;
+    if (oslot < order_len) dq = order ? order[oslot] : oslot;
+  }
+  const size_t dqm = ((size_t)b * Lq + (dq >= 0 ? dq : 0)) * M + m;
+  int qpf = -1;
+  {
+    const int pslot = (tile + kWinPrefetchTiles) * kTileQ + dql;
+    if (pslot < order_len) qpf = order ? order[pslot] : pslot;
+  }
+  const size_t qm_pf = ((size_t)b * Lq + (qpf >= 0 ? qpf : 0)) * M + m;
+  if (qpf >= 0 && dslot == 0) prefetch_l2(grad_out + qm_pf * 32);
+  // grad_out rows of the tile -> shared memory as fp32 (C floats per 16-byte global chunk)
+  for (int i = t; i < kTileQ * G; i += kWinThreads) {
+    const int gql = i / G, gj = i % G;
+    const int oslot = tile * kTileQ + gql;
+    int gq = -1;
+    if (oslot < order_len) gq = order ? order[oslot] : oslot;
+    float gv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) gv[c] = 0.f;
+    if (gq >= 0) RT::load_stream(grad_out + (((size_t)b * Lq + gq) * M + m) * 32 + gj * C, gv);
+#pragma unroll
+    for (int c = 0; c < C; c += 4)
+      *reinterpret_cast<float4*>(go_s + gql * 32 + gj * C + c) = make_float4(gv[c], gv[c + 1], gv[c + 2], gv[c + 3]);
+  }
+  WinAlloc<kL> wa;
+  WinPoint pts[Cfg::NLV][4];
+  int rank[Cfg::NLV][4];
+  win_front_end<VT, kL, kWinPool, true>(value_img, loc, attw, dq, dqm, qpf, qm_pf, m, M, lv, pool, rec, bb, rowoff, hist, wa, pts, rank, tphase);
+  if (t < 2) rowoff[kWinPool + t] = -1;
+  if (t >= 32 && t < 32 + kL) { lvf[t - 32] = (float)lv.W[t - 32]; lvf[8 + t - 32] = (float)lv.H[t - 32]; }
+  __syncthreads();  // hist complete, records visible
+  WIN_T(9, tphase);  // allocation, staging issue, records, histogram
+
+  // ---- exclusive scan of the per-cell counts, in place -----------------------------------------
+  {
+    int v[Cfg::SPT], sum = 0;
+#pragma unroll
+    for (int k = 0; k < Cfg::SPT; ++k) { v[k] = hist[t * Cfg::SPT + k]; sum += v[k]; }
+    int inc = sum;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc, s);
+      if (lane >= s) inc += n;
+    }
+    if (lane == 31) misc[warp] = inc;
+    __syncthreads();
+    int run = inc - sum;
+    for (int w = 0; w < warp; ++w) run += misc[w];
+#pragma unroll
+    for (int k = 0; k < Cfg::SPT; ++k) { hist[t * Cfg::SPT + k] = run; run += v[k]; }
+    if (t == kWinThreads - 1) misc[8] = run;
+    __syncthreads();
+  }
+  // ---- place the sample ids at their sorted positions ---------------------------------------------
+#pragma unroll
+  for (int li = 0; li < Cfg::NLV; ++li) {
+    const int l = dslot + 4 * li;
+    if (l < kL) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (rank[li][i] >= 0) {
+          const int code = __float_as_int(rec[dql * Cfg::REC_STRIDE + l * 4 + i].x);
+          sorted[hist[code & 0xffff] + rank[li][i]] = (unsigned short)(dql * LP + l * 4 + i);
+        }
+    }
+  }
+  WIN_T(10, tphase);  // scan + placement
+  cp_async_wait_all();
+  __syncthreads();  // windows, sorted list, grad_out rows are in shared memory
+  WIN_T(11, tphase);  // wait for the windows
+
+  // ---- sorted pass: one 4-lane group (8 channels per lane) per contiguous chunk of the cell-sorted samples ----
+  {
+    using SL = SortLane<VT>;
+    constexpr int SG = 4, SC = 8, SNG = kWinThreads / SG;
+    const int sg = lane >> 2, sj = lane & 3;
+    const int oA = SL::chunk_a(sg, sj) * 16, oB = SL::chunk_b(sg, sj) * 16;  // byte offsets in a 128-byte fp32 row
+    const unsigned char* pool_v = pool + SL::pool_offset(sg, sj);
+    float* gvalue_a = grad_value + img + oA / 4;
+    float* gvalue_b = grad_value + img + oB / 4;
+    const unsigned char* go_a = reinterpret_cast<const unsigned char*>(go_s) + oA;
+    const unsigned char* go_b = reinterpret_cast<const unsigned char*>(go_s) + oB;
+    const int total = misc[8];
+    const int chunk = (((total + SNG - 1) / SNG) + 3) & ~3;  // multiple of the batch size
+    const int gi = warp * 8 + sg;
+    const int i0 = min(total, gi * chunk), i1 = min(total, i0 + chunk);
+    const unsigned gmask = 0xfu << (sg * 4);
+    // channel pairs: every FMA below is one FFMA2
+    constexpr int SP = SC / 2;
+    float2 V00[SP], V01[SP], V10[SP], V11[SP], A0[SP], A1[SP], B0[SP], B1[SP];
+    const float2 zero2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < SP; ++c) V00[c] = V01[c] = V10[c] = V11[c] = A0[c] = A1[c] = B0[c] = B1[c] = zero2;
+    int cur0 = -2, cur1 = -2;
+    auto flush = [&](const int row, const float2 (&acc)[SP]) {
+      const int off = rowoff[row];
+      if (off >= 0) {
+        red_add_f4(gvalue_a + off, acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+        red_add_f4(gvalue_b + off, acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+      }
+    };
+    auto load_row = [&](const int row, float2 (&v)[SP]) {
+      float t8[SC];
+      SL::lds(pool_v + row * ROWB, t8);
+#pragma unroll
+      for (int c = 0; c < SP; ++c) v[c] = make_float2(t8[2 * c], t8[2 * c + 1]);
+    };
+    auto rec_slot = [&](const int sid) { const int sq = sid / LP; return sq * Cfg::REC_STRIDE + (sid - sq * LP); };
+    float4 rnext = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i0 < i1) rnext = rec[rec_slot(sorted[i0])];
+    for (int ib = i0; ib < i1; ib += 4) {
+      const uint2 packed = *reinterpret_cast<const uint2*>(sorted + ib);  // 4 sample ids (ib is a multiple of 4)
+      const int nb = min(4, i1 - ib);
+      int nsid = 0;
+      if (ib + 4 < i1) nsid = sorted[ib + 4];
+      float pgx[4], pgy[4], pga[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        pgx[u] = pgy[u] = pga[u] = 0.f;
+        if (u < nb) {  // group-uniform
+          const int sid = (int)(((u < 2 ? packed.x : packed.y) >> ((u & 1) * 16)) & 0xffffu);
+          const int sq = sid / LP, l = (sid - sq * LP) >> 2;
+          const float4 r = rnext;
+          // grad_out row of the sample's query; the next sample's record is fetched one step ahead
+          const float4 ga4 = *reinterpret_cast<const float4*>(go_a + sq * 128);
+          const float4 gb4 = *reinterpret_cast<const float4*>(go_b + sq * 128);
+          {
+            const int sidn = u == 3 ? nsid
+                                    : (int)((((u + 1) < 2 ? packed.x : packed.y) >> (((u + 1) & 1) * 16)) & 0xffffu);
+            if (u + 1 < nb || (u == 3 && ib + 4 < i1)) rnext = rec[rec_slot(sidn)];
+          }
+          const int code = __float_as_int(r.x);
+          const int row0 = code & 0xffff, row1 = code >> 16;
+          if (row0 != cur0) {
+            const bool adj = (row0 == cur0 + 1);
+            if (cur0 >= 0) {
+              flush(cur0, A0);
+              flush(cur1, B0);
+              if (!adj) {
+                flush(cur0 + 1, A1);
+                flush(cur1 + 1, B1);
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < SP; ++c) {
+              A0[c] = adj ? A1[c] : zero2;
+              B0[c] = adj ? B1[c] : zero2;
+              A1[c] = zero2;
+              B1[c] = zero2;
+            }
+            load_row(row0, V00);
+            load_row(row0 + 1, V01);
+            load_row(row1, V10);
+            load_row(row1 + 1, V11);
+            cur0 = row0; cur1 = row1;
+          }
+          const float lh = r.y, lw = r.z, a = r.w;
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          const float2 go[SP] = {make_float2(ga4.x, ga4.y), make_float2(ga4.z, ga4.w), make_float2(gb4.x, gb4.y),
+                                 make_float2(gb4.z, gb4.w)};
+          // grad_value partial sums (cuh:125,134,143,152): independent of the value rows, so they cover
+          // the latency of a window reload
+          const float c00 = hh * hw, c01 = hh * lw, c10 = lh * hw, c11 = lh * lw;
+          const float w00 = c00 * a, w01 = c01 * a, w10 = c10 * a, w11 = c11 * a;
+          const float2 w00p = make_float2(w00, w00), w01p = make_float2(w01, w01), w10p = make_float2(w10, w10),
+                       w11p = make_float2(w11, w11);
+#pragma unroll
+          for (int c = 0; c < SP; ++c) {
+            A0[c] = ffma2(w00p, go[c], A0[c]); A1[c] = ffma2(w01p, go[c], A1[c]);
+            B0[c] = ffma2(w10p, go[c], B0[c]); B1[c] = ffma2(w11p, go[c], B1[c]);
+          }
+          float2 e00 = zero2, e01 = zero2, e10 = zero2, e11 = zero2;
+#pragma unroll
+          for (int c = 0; c < SP; ++c) {
+            e00 = ffma2(go[c], V00[c], e00); e01 = ffma2(go[c], V01[c], e01);
+            e10 = ffma2(go[c], V10[c], e10); e11 = ffma2(go[c], V11[c], e11);
+          }
+          const float d00 = e00.x + e00.y, d01 = e01.x + e01.y, d10 = e10.x + e10.y, d11 = e11.x + e11.y;
+          // grad_attn_weight (cuh:156), grad_sampling_loc (cuh:157-158): this lane's channels
+          pga[u] = fmaf(c00, d00, fmaf(c01, d01, fmaf(c10, d10, c11 * d11)));
+          pgx[u] = (a * lvf[l]) * fmaf(hh, d01 - d00, lh * (d11 - d10));
+          pgy[u] = (a * lvf[8 + l]) * fmaf(hw, d10 - d00, lw * (d11 - d01));
+        }
+      }
+      const float gx = group_reduce_scatter<4>(pgx, sj, gmask);
+      const float gy = group_reduce_scatter<4>(pgy, sj, gmask);
+      const float ga = group_reduce_scatter<4>(pga, sj, gmask);
+      if (sj < nb) {  // lane sj owns sample ib + sj: park its gradients in the sample's record slot
+        const int sid = (int)(((sj < 2 ? packed.x : packed.y) >> ((sj & 1) * 16)) & 0xffffu);
+        rec[rec_slot(sid)] = make_float4(gx, gy, ga, 0.f);
+      }
+    }
+    if (cur0 >= 0) {
+      flush(cur0, A0);
+      flush(cur1, B0);
+      flush(cur0 + 1, A1);
+      flush(cur1 + 1, B1);
+    }
+  }
+  const int g = lane / G, j = lane % G;
+  float* gvalue_j = grad_value + img + j * C;
+
+#ifdef MSDA_WIN_TIMING
+  __syncthreads();
+  WIN_T(12, tphase);  // sorted pass
+#endif
+  // ---- direct pass: levels that did not get a window, query-major from global memory -------------------
+  bool all_win = true;
+#pragma unroll
+  for (int l = 0; l < kL; ++l) all_win = all_win && wa.base[l] >= 0;
+  if (!all_win) {
+    const VT* value_j = value_img + j * C;
+    for (int ql = warp * GPW + g; ql < kTileQ; ql += NG) {
+      float go[C];
+#pragma unroll
+      for (int c = 0; c < C; c += 4) {
+        const float4 gq = *reinterpret_cast<const float4*>(go_s + ql * 32 + j * C + c);
+        go[c] = gq.x; go[c + 1] = gq.y; go[c + 2] = gq.z; go[c + 3] = gq.w;
+      }
+#pragma unroll
+      for (int l = 0; l < kL; ++l) {
+        if (wa.base[l] >= 0) continue;  // block-uniform
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4* slot = rec + ql * Cfg::REC_STRIDE + l * 4 + i;
+          const float4 r = *slot;
+          const int code = __float_as_int(r.x);
+          const float lh = r.y, lw = r.z, a = r.w;
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          const float a_hh = a * hh, a_lh = a * lh;
+          const ptrdiff_t o0 = (ptrdiff_t)(code & ~31);
+          const ptrdiff_t o2 = o0 + (ptrdiff_t)(lv.W[l] * M32);
+          float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (code & (1 << k)) {
+              const ptrdiff_t o = ((k & 2) ? o2 : o0) + ((k & 1) ? M32 : 0);
+              float v[C];
+              RT::load(value_j + o, v);
+              const float tt = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
+#pragma unroll
+              for (int c = 0; c < C; c += 4)
+                red_add_f4(gvalue_j + o + c, tt * go[c], tt * go[c + 1], tt * go[c + 2], tt * go[c + 3]);
+              float sdot = 0.f;
+#pragma unroll
+              for (int c = 0; c < C; ++c) sdot = fmaf(go[c], v[c], sdot);
+              d[k] = sdot;
+            }
+          }
+          float ga = hh * (hw * d[0] + lw * d[1]) + lh * (hw * d[2] + lw * d[3]);
+          float gx = (a * (float)lv.W[l]) * (hh * (d[1] - d[0]) + lh * (d[3] - d[2]));
+          float gy = (a * (float)lv.H[l]) * (hw * (d[2] - d[0]) + lw * (d[3] - d[1]));
+#pragma unroll
+          for (int s = G / 2; s >= 1; s >>= 1) {
+            ga += __shfl_xor_sync(0xffffffffu, ga, s);
+            gx += __shfl_xor_sync(0xffffffffu, gx, s);
+            gy += __shfl_xor_sync(0xffffffffu, gy, s);
+          }
+          __syncwarp();
+          if (j == 0) *slot = make_float4(gx, gy, ga, 0.f);
+        }
+      }
+    }
+  }
+  __syncthreads();  // every sample's gradients are parked in its record slot
+  WIN_T(13, tphase);  // direct pass
+#ifdef MSDA_WIN_TIMING
+  if (threadIdx.x == 0) atomicAdd(&g_win_timing[15], 1ull);
+#endif
+
+  // ---- write-out: same thread <-> (level, query) mapping as the decode ------------------------------------
+  if (dq >= 0) {
+#pragma unroll
+    for (int li = 0; li < Cfg::NLV; ++li) {
+      const int l = dslot + 4 * li;
+      if (l < kL) {
+        float4 r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          r[i] = rec[dql * Cfg::REC_STRIDE + l * 4 + i];
+          if (!pts[li][i].in) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // skipped sample: slot still holds its record
+        }
+        float* gl = grad_loc + (dqm * LP + l * 4) * 2;
+        st_stream_f4(gl, make_float4(r[0].x, r[0].y, r[1].x, r[1].y));
+        st_stream_f4(gl + 4, make_float4(r[2].x, r[2].y, r[3].x, r[3].y));
+        st_stream_f4(grad_attw + dqm * LP + l * 4, make_float4(r[0].z, r[1].z, r[2].z, r[3].z));
+      }
+    }
+  }
+}
+
+}  // namespace msda

@@ -1,7 +1,12 @@
-// msda_host.h — host-side helpers shared by the launch code (defined in msda_capi.cu).
+// msda_host.h — host-side declarations shared by the translation units of libmsda_b200.so.
+// msda_capi.cu holds the C entry points, validation and kernel selection; the kernels are instantiated
+// and launched from msda_launch_{d32,win,other}.cu so that nvcc can compile them in parallel.
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
+
+#include "msda_common.cuh"
 
 namespace msda {
 
@@ -11,5 +16,50 @@ int fail(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 // Counts the launch (msda_launch_count) and reports a launch-time error, if any.
 int after_launch(const char* what);
+
+// One validated call: dimensions, resolved level table, optional query order, flags.
+struct Problem {
+  MsdaDims d;
+  MsdaLevels lv;
+  const int32_t* order;
+  int order_len;
+  uint32_t flags;
+};
+
+// Few (query, head) pairs (decoder cross-attention): one warp per pair instead of one lane group.
+inline bool use_split(const Problem& pb) {
+  return !(pb.flags & MSDA_FLAG_NO_SPLIT) &&
+         (long long)pb.d.batch * pb.d.num_query * pb.d.num_heads <= 65536 && pb.d.num_levels >= 2 &&
+         pb.d.num_levels <= 6;
+}
+
+// ---- head_dim 32, 4 points, 1..6 levels; VT = float | __nv_bfloat16 (explicitly instantiated) ----
+// msda_launch_d32.cu: L1-gather kernels (tiled for large problems, split for small ones, opt-in
+// pre-aggregating backward).
+template <typename VT>
+int fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const float* loc, const float* attw, VT* out);
+template <typename VT, bool kScatter>
+int bwd_d32(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
+            const float* attw, float* gv, float* gl, float* ga);
+// msda_launch_win.cu: shared-memory window kernels (large problems).
+template <typename VT>
+int fwd_d32_win(cudaStream_t s, const Problem& pb, const VT* value, const float* loc, const float* attw, VT* out);
+template <typename VT>
+int bwd_d32_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
+                const float* attw, float* gv, float* gl, float* ga);
+
+// ---- msda_launch_other.cu: any-shape kernels, deterministic grad_value, index probe ----
+template <typename TV, typename TA>
+int fwd_generic(cudaStream_t s, const Problem& pb, const TV* value, const TA* loc, const TA* attw, TV* out);
+template <typename TV, typename TA>
+int bwd_generic(cudaStream_t s, const Problem& pb, bool scatter, const TV* go, const TV* value, const TA* loc,
+                const TA* attw, TA* gv, TA* gl, TA* ga);
+template <typename TV>
+int det_grad_value(cudaStream_t s, const Problem& pb, const TV* go, const float* loc, const float* attw,
+                   float* gv, void* workspace, size_t workspace_bytes);
+size_t det_workspace_bytes(int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                           int num_query, int num_point);
+int corners_probe(cudaStream_t s, const MsdaLevels& lv, const float* loc, int32_t* corners, long long n,
+                  int num_levels, int num_point);
 
 }  // namespace msda

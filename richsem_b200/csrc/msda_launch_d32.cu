@@ -1,0 +1,143 @@
+// msda_launch_d32.cu — instantiates and launches the L1-gather D=32 kernels (msda_d32.cuh,
+// msda_d32_agg.cuh): tiled, split and the opt-in pre-aggregating backward.
+#include "msda_host.h"
+#include "msda_d32.cuh"
+#include "msda_d32_agg.cuh"
+
+namespace msda {
+namespace {
+
+// ---- tuned D=32 dispatch (fp32 and bf16 value) -----------------------------------------------
+template <typename VT, int kL, int kM>
+int launch_fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const float* loc,
+                   const float* attw, VT* out) {
+  using Cfg = msda::D32Cfg<VT, kL * 4>;
+  const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
+  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
+  msda::msda_fwd_d32_kernel<VT, kL, 4, kM><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
+      value, loc, attw, out, pb.order, pb.order_len, pb.lv, pb.d.spatial_size, pb.d.num_heads,
+      pb.d.num_query);
+  return after_launch("msda_fwd_d32_kernel");
+}
+template <typename VT, int kL, int kM, bool kScatter>
+int launch_bwd_d32(cudaStream_t s, const Problem& pb, const VT* grad_out, const VT* value,
+                   const float* loc, const float* attw, float* gv, float* gl, float* ga) {
+  using Cfg = msda::D32Cfg<VT, kL * 4>;
+  const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
+  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
+  msda::msda_bwd_d32_kernel<VT, kL, 4, kM, kScatter><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
+      grad_out, value, loc, attw, gv, gl, ga, pb.order, pb.order_len, pb.lv, pb.d.spatial_size,
+      pb.d.num_heads, pb.d.num_query);
+  return after_launch("msda_bwd_d32_kernel");
+}
+
+template <typename VT, int kL, int kM>
+int launch_fwd_split(cudaStream_t s, const Problem& pb, const VT* value, const float* loc,
+                     const float* attw, VT* out) {
+  constexpr int QPB = msda::kSplitThreads / 32;
+  dim3 grid(((pb.d.num_query + QPB - 1) / QPB) * pb.d.num_heads, pb.d.batch);
+  msda::msda_fwd_d32_split_kernel<VT, kL, 4, kM><<<grid, msda::kSplitThreads, 0, s>>>(
+      value, loc, attw, out, pb.lv, pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
+  return after_launch("msda_fwd_d32_split_kernel");
+}
+template <typename VT, int kL, int kM, bool kScatter>
+int launch_bwd_split(cudaStream_t s, const Problem& pb, const VT* grad_out, const VT* value,
+                     const float* loc, const float* attw, float* gv, float* gl, float* ga) {
+  constexpr int QPB = msda::kSplitThreads / 32;
+  dim3 grid(((pb.d.num_query + QPB - 1) / QPB) * pb.d.num_heads, pb.d.batch);
+  msda::msda_bwd_d32_split_kernel<VT, kL, 4, kM, kScatter><<<grid, msda::kSplitThreads, 0, s>>>(
+      grad_out, value, loc, attw, gv, gl, ga, pb.lv, pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
+  return after_launch("msda_bwd_d32_split_kernel");
+}
+
+template <typename VT, int kL, int kM>
+int launch_bwd_agg(cudaStream_t s, const Problem& pb, const VT* grad_out, const VT* value,
+                   const float* loc, const float* attw, float* gv, float* gl, float* ga) {
+  using Cfg = msda::AggCfg<kL>;
+  auto kern = msda::msda_bwd_d32_agg_kernel<VT, kL, kM>;
+  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_bwd_d32_agg_kernel)");
+  const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
+  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
+  kern<<<grid, msda::kAggThreads, Cfg::SMEM_BYTES, s>>>(grad_out, value, loc, attw, gv, gl, ga, pb.order,
+                                                        pb.order_len, pb.lv, pb.d.spatial_size,
+                                                        pb.d.num_heads, pb.d.num_query);
+  return after_launch("msda_bwd_d32_agg_kernel");
+}
+
+// On-chip pre-aggregation of grad_value (msda_d32_agg.cuh) cuts the L2 reductions 8.7x but, as
+// measured on B200 (profiles/r1_bwd_agg.md), its counting sort makes it latency-bound: 0.62 ms
+// against 0.47 ms for the plain kernel at the headline shape.  It stays opt-in.
+inline bool use_aggregate(const Problem& pb) {
+  if (pb.flags & MSDA_FLAG_NO_AGGREGATE) return false;
+  return (pb.flags & MSDA_FLAG_AGGREGATE) != 0;
+}
+
+#define MSDA_SWITCH_L(L_, CALL)                                                              \
+  switch (L_) {                                                                              \
+    case 1: return CALL(1);                                                                  \
+    case 2: return CALL(2);                                                                  \
+    case 3: return CALL(3);                                                                  \
+    case 4: return CALL(4);                                                                  \
+    case 5: return CALL(5);                                                                  \
+    case 6: return CALL(6);                                                                  \
+    default: return fail(MSDA_ERR_UNSUPPORTED, "no tuned kernel for num_levels=%d", L_);      \
+  }
+
+}  // namespace
+
+template <typename VT>
+int fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const float* loc, const float* attw,
+            VT* out) {
+  if (use_split(pb)) {
+    if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_fwd_split<VT, 4, 8>(s, pb, value, loc, attw, out);
+#define CALL(L) launch_fwd_split<VT, L, 0>(s, pb, value, loc, attw, out)
+    MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+  }
+  // the DINO / RichSem configuration (8 heads, 4 or 5 levels) gets the head count baked in
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_fwd_d32<VT, 4, 8>(s, pb, value, loc, attw, out);
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 5) return launch_fwd_d32<VT, 5, 8>(s, pb, value, loc, attw, out);
+#define CALL(L) launch_fwd_d32<VT, L, 0>(s, pb, value, loc, attw, out)
+  MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+}
+template <typename VT, bool kScatter>
+int bwd_d32(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
+            const float* attw, float* gv, float* gl, float* ga) {
+  if (kScatter && use_aggregate(pb) && (!use_split(pb) || (pb.flags & MSDA_FLAG_AGGREGATE))) {
+    if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_bwd_agg<VT, 4, 8>(s, pb, go, value, loc, attw, gv, gl, ga);
+#define CALL(L) launch_bwd_agg<VT, L, 0>(s, pb, go, value, loc, attw, gv, gl, ga)
+    MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+  }
+  if (use_split(pb)) {
+    if (pb.d.num_heads == 8 && pb.d.num_levels == 4)
+      return launch_bwd_split<VT, 4, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
+#define CALL(L) launch_bwd_split<VT, L, 0, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
+    MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+  }
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 4)
+    return launch_bwd_d32<VT, 4, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 5)
+    return launch_bwd_d32<VT, 5, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
+#define CALL(L) launch_bwd_d32<VT, L, 0, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
+  MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+}
+
+
+template int fwd_d32<float>(cudaStream_t, const Problem&, const float*, const float*, const float*, float*);
+template int fwd_d32<__nv_bfloat16>(cudaStream_t, const Problem&, const __nv_bfloat16*, const float*, const float*,
+                                    __nv_bfloat16*);
+#define INST_BWD(VT, SC)                                                                                   \
+  template int bwd_d32<VT, SC>(cudaStream_t, const Problem&, const VT*, const VT*, const float*, const float*, \
+                               float*, float*, float*);
+INST_BWD(float, true)
+INST_BWD(float, false)
+INST_BWD(__nv_bfloat16, true)
+INST_BWD(__nv_bfloat16, false)
+#undef INST_BWD
+
+}  // namespace msda

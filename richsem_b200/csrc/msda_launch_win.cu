@@ -1,0 +1,88 @@
+// msda_launch_win.cu — instantiates and launches the shared-memory window kernels (msda_d32_win.cuh).
+#include "msda_host.h"
+#include "msda_d32_win.cuh"
+
+namespace msda {
+namespace {
+
+template <typename VT, int kL, int kM>
+int launch_fwd_win(cudaStream_t s, const Problem& pb, const VT* value, const float* loc,
+                   const float* attw, VT* out) {
+  using Cfg = WinCfg<VT, kL, kWinPoolFwd>;
+  auto kern = msda_fwd_d32_win_kernel<VT, kL, kM>;
+  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::FWD_SMEM);
+  if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_fwd_d32_win_kernel)");
+  const int tiles = (pb.order_len + kTileQ - 1) / kTileQ;
+  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
+  kern<<<grid, kWinThreads, Cfg::FWD_SMEM, s>>>(value, loc, attw, out, pb.order, pb.order_len, pb.lv,
+                                                      pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
+  return after_launch("msda_fwd_d32_win_kernel");
+}
+
+
+template <typename VT, int kL, int kM>
+int launch_bwd_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
+                   const float* attw, float* gv, float* gl, float* ga) {
+  using Cfg = WinCfg<VT, kL, kWinPoolBwd>;
+  auto kern = msda_bwd_d32_win_kernel<VT, kL, kM>;
+  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BWD_SMEM);
+  if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_bwd_d32_win_kernel)");
+  const int tiles = (pb.order_len + kTileQ - 1) / kTileQ;
+  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
+  kern<<<grid, kWinThreads, Cfg::BWD_SMEM, s>>>(go, value, loc, attw, gv, gl, ga, pb.order, pb.order_len, pb.lv,
+                                                pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
+  return after_launch("msda_bwd_d32_win_kernel");
+}
+
+#define MSDA_SWITCH_L(L_, CALL)                                                              \
+  switch (L_) {                                                                              \
+    case 1: return CALL(1);                                                                  \
+    case 2: return CALL(2);                                                                  \
+    case 3: return CALL(3);                                                                  \
+    case 4: return CALL(4);                                                                  \
+    case 5: return CALL(5);                                                                  \
+    case 6: return CALL(6);                                                                  \
+    default: return fail(MSDA_ERR_UNSUPPORTED, "no tuned kernel for num_levels=%d", L_);      \
+  }
+
+}  // namespace
+
+template <typename VT>
+int fwd_d32_win(cudaStream_t s, const Problem& pb, const VT* value, const float* loc, const float* attw, VT* out) {
+  // the DINO / RichSem configuration (8 heads, 4 levels) gets the head count baked in
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_fwd_win<VT, 4, 8>(s, pb, value, loc, attw, out);
+#define CALL(L) launch_fwd_win<VT, L, 0>(s, pb, value, loc, attw, out)
+  MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+}
+
+template <typename VT>
+int bwd_d32_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
+                const float* attw, float* gv, float* gl, float* ga) {
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_bwd_win<VT, 4, 8>(s, pb, go, value, loc, attw, gv, gl, ga);
+#define CALL(L) launch_bwd_win<VT, L, 0>(s, pb, go, value, loc, attw, gv, gl, ga)
+  MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+}
+
+template int fwd_d32_win<float>(cudaStream_t, const Problem&, const float*, const float*, const float*, float*);
+template int fwd_d32_win<__nv_bfloat16>(cudaStream_t, const Problem&, const __nv_bfloat16*, const float*,
+                                        const float*, __nv_bfloat16*);
+
+template int bwd_d32_win<float>(cudaStream_t, const Problem&, const float*, const float*, const float*, const float*,
+                                float*, float*, float*);
+template int bwd_d32_win<__nv_bfloat16>(cudaStream_t, const Problem&, const __nv_bfloat16*, const __nv_bfloat16*,
+                                        const float*, const float*, float*, float*, float*);
+
+#ifdef MSDA_WIN_TIMING
+// debug builds only: copies and clears the phase-timing accumulators
+extern "C" int msda_debug_win_timing(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_win_timing, sizeof(unsigned long long) * 16);
+  unsigned long long z[16] = {0};
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_win_timing, z, sizeof(z));
+  return (int)e;
+}
+#endif
+
+}  // namespace msda
