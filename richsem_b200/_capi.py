@@ -27,6 +27,7 @@ FLAG_NO_AGGREGATE = 0x20
 FLAG_AGGREGATE = 0x40
 FLAG_NO_WINDOW = 0x80
 FLAG_WINDOW_FWD = 0x100
+FLAG_LDG256 = 0x200
 MAX_LEVELS = 16
 
 _vp, _i, _i64p = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)

@@ -40,7 +40,7 @@ def test_extension_is_loaded_from_the_tree():
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-@pytest.mark.parametrize("path", ["auto", "window", "tiled", "aggregate", "generic"])
+@pytest.mark.parametrize("path", ["auto", "window", "tiled", "tiled256", "aggregate", "generic"])
 def test_golden_forward_backward(case, path):
     """auto = what the library picks (warp-per-query "split" kernels at these sizes for D=32);
     window = the shared-memory window kernels used for large problems; tiled = their L1-gather
@@ -52,6 +52,7 @@ def test_golden_forward_backward(case, path):
     v, shp, st, loc, w, go = _to_dev(g)
     flags = {"auto": 0, "window": _capi.FLAG_NO_SPLIT | _capi.FLAG_WINDOW_FWD,
              "tiled": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_AGGREGATE | _capi.FLAG_NO_WINDOW,
+             "tiled256": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW | _capi.FLAG_LDG256,
              "aggregate": _capi.FLAG_AGGREGATE | _capi.FLAG_NO_WINDOW, "generic": _capi.FLAG_FORCE_GENERIC}[path]
     out = _ext().ms_deform_attn_forward(v, shp, st, loc, w, 64, _flags=flags)
     gv, gl, ga = _ext().ms_deform_attn_backward(v, shp, st, loc, w, go, 64, _flags=flags)
