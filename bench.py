@@ -41,6 +41,7 @@ WORKLOADS = {
     # name: (image hw, layers, batch/GPU, kind, Lq (None = S), value dtype)
     "encoder6": ((800, 1333), 6, 2, "E", None, "f32"),
     "encoder1": ((800, 1333), 1, 2, "E", None, "f32"),
+    "encoder6_bf16": ((800, 1333), 6, 2, "E", None, "bf16"),
     "decoder6": ((800, 1333), 6, 2, "Dn", 1100, "bf16"),
     "decoder6_f32": ((800, 1333), 6, 2, "Dn", 1100, "f32"),
     "encoder1_hr1333": ((1333, 1333), 1, 2, "E", None, "f32"),
