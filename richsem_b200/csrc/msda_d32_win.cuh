@@ -68,6 +68,14 @@ __device__ unsigned long long g_win_timing[16];
 #define WIN_T(k, t0) do { } while (0)
 #endif
 
+// Index checks for debug builds (MSDA_NVCC_EXTRA=-DMSDA_WIN_CHECKS): compute-sanitizer is not available on
+// the GPU pool, so the shared-memory indices of these kernels are asserted by hand; a failed check traps.
+#ifdef MSDA_WIN_CHECKS
+#define WIN_CHECK(cond) do { if (!(cond)) asm volatile("trap;"); } while (0)
+#else
+#define WIN_CHECK(cond) do { } while (0)
+#endif
+
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // 16-byte global->shared copy that bypasses L1 and registers; src_bytes = 0 writes zeros.
@@ -161,7 +169,7 @@ __device__ __forceinline__ void win_allocate(const int* bb, WinAlloc<kL>& wa) {
 // Stages the windows of all allocated levels: warp w copies window lines w, w+8, ... of each level.
 // rowoff (backward only): per pool row, the element offset of the row inside the image's value block,
 // or -1 for rows outside the image.
-template <typename VT, int kL, bool kRowOff>
+template <typename VT, int kL, bool kRowOff, int kWinPoolCheck>
 __device__ __forceinline__ void win_stage(const WinAlloc<kL>& wa, const MsdaLevels& lv, const VT* value_img,
                                           const int m, const int M, unsigned char* pool, int* rowoff) {
   constexpr int ROWB = WinRow<VT>::ROWB, G = ROWB / 16, EPL = 16 / (int)sizeof(VT);  // elements per 16 B
@@ -180,6 +188,7 @@ __device__ __forceinline__ void win_stage(const WinAlloc<kL>& wa, const MsdaLeve
       for (int rw = rw0; rw < bw; rw += 32 / G) {
         const bool inb = hin && (unsigned)(wa.wm[l] + rw) < (unsigned)W;
         const int off = off_l + rw * (M * 32);
+        WIN_CHECK(row_l + rw >= 0 && row_l + rw < kWinPoolCheck);
         cp_async16(pool_s + (unsigned)((row_l + rw) * ROWB + jj * 16), value_img + (inb ? off : 0) + jj * EPL,
                    inb ? 16 : 0);
         if (kRowOff && jj == 0) rowoff[row_l + rw] = inb ? off : -1;
@@ -285,7 +294,7 @@ __device__ __forceinline__ void win_front_end(const VT* __restrict__ value_img, 
   __syncthreads();
   WIN_T(kBwd ? 8 : 0, tph);  // decode + bounding boxes
   win_allocate<kL, kWinPool>(bb, wa);
-  win_stage<VT, kL, kBwd>(wa, lv, value_img, m, M, pool, rowoff);
+  win_stage<VT, kL, kBwd, kWinPool>(wa, lv, value_img, m, M, pool, rowoff);
 #pragma unroll
   for (int li = 0; li < Cfg::NLV; ++li) {
     const int l = slot + 4 * li;
@@ -299,6 +308,8 @@ __device__ __forceinline__ void win_front_end(const VT* __restrict__ value_img, 
       for (int i = 0; i < 4; ++i) {
         const int code = win_record_code<kWinPool>(pts[li][i], base, bw, hm, wm, H, W, st, m, M);
         rank[li][i] = -1;
+        WIN_CHECK(base < 0 || ((code & 0xffff) + 1 <= kWinPool + 1 && (code >> 16) + 1 <= kWinPool + 1));
+        WIN_CHECK(base < 0 || !pts[li][i].in || ((code >> 16) + 1 < kWinPool && (code & 0xffff) >= base));
         if (kBwd && base >= 0 && pts[li][i].in) rank[li][i] = atomicAdd(&hist[code & 0xffff], 1);
         rec[ql * Cfg::REC_STRIDE + l * 4 + i] =
             make_float4(__int_as_float(code), pts[li][i].lh, pts[li][i].lw, pts[li][i].in ? pts[li][i].a : 0.f);
@@ -593,6 +604,7 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
       for (int i = 0; i < 4; ++i)
         if (rank[li][i] >= 0) {
           const int code = __float_as_int(rec[dql * Cfg::REC_STRIDE + l * 4 + i].x);
+          WIN_CHECK(hist[code & 0xffff] + rank[li][i] >= 0 && hist[code & 0xffff] + rank[li][i] < misc[8]);
           sorted[hist[code & 0xffff] + rank[li][i]] = (unsigned short)(dql * LP + l * 4 + i);
         }
     }
@@ -626,7 +638,9 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
     for (int c = 0; c < SP; ++c) V00[c] = V01[c] = V10[c] = V11[c] = A0[c] = A1[c] = B0[c] = B1[c] = zero2;
     int cur0 = -2, cur1 = -2;
     auto flush = [&](const int row, const float2 (&acc)[SP]) {
+      WIN_CHECK(row >= 0 && row < kWinPool + 2);
       const int off = rowoff[row];
+      WIN_CHECK(off < 0 || (off % 32 == 0 && off / 32 < S * M));
       if (off >= 0) {
         red_add_f4(gvalue_a + off, acc[0].x, acc[0].y, acc[1].x, acc[1].y);
         red_add_f4(gvalue_b + off, acc[2].x, acc[2].y, acc[3].x, acc[3].y);
@@ -664,6 +678,7 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
           }
           const int code = __float_as_int(r.x);
           const int row0 = code & 0xffff, row1 = code >> 16;
+          WIN_CHECK(sid < kTileQ * LP && row0 >= cur0 && row1 + 1 < kWinPool && row1 > row0);
           if (row0 != cur0) {
             const bool adj = (row0 == cur0 + 1);
             if (cur0 >= 0) {
