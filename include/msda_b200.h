@@ -71,6 +71,8 @@ extern "C" {
 #define MSDA_FLAG_NO_AGGREGATE 0x20u           /* backward: never pre-aggregate grad_value on chip (comparison)    */
 #define MSDA_FLAG_AGGREGATE 0x40u              /* backward: pre-aggregate even without a query_order (testing)     */
 #define MSDA_FLAG_NO_WINDOW 0x80u              /* backward: keep the L1-gather tiled kernel instead of the shared-memory window kernel */
+#define MSDA_FLAG_BWD_HALVES 0x800u            /* backward: gather kernel + cell-sorted grad_value kernel instead of the fused window kernel */
+#define MSDA_FLAG_NO_GRAD_VALUE 0x400u         /* backward: value needs no gradient; grad_value is not touched and may be NULL   */
 #define MSDA_FLAG_LDG256 0x200u                /* forward, fp32: 256-bit gathers, 4 lanes per (query, head) (opt-in, comparison)  */
 #define MSDA_FLAG_WINDOW_FWD 0x100u            /* forward: use the shared-memory window kernel (opt-in, slower on B200)        */
 #define MSDA_FLAG_NO_SPLIT 0x8u               /* small problems: keep the lane-group-per-query kernels (testing)    */

@@ -146,7 +146,10 @@ def _workspace(nbytes, device):
 
 
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-                            im2col_step, _flags: int = 0):
+                            im2col_step, _flags: int = 0, _need_grad_value: bool = True):
+    """Same arguments and return value as the reference's binding (vision.cpp:15).  `_need_grad_value=False`
+    (an addition; the autograd Function passes `ctx.needs_input_grad[0]`) skips the grad_value scatter — the
+    more expensive half of the backward — and returns None in its place."""
     _check_inputs((("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                    ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)))
     n, s, m, d, nl, lq, npt = _dims(value, spatial_shapes, sampling_loc, attn_weight, im2col_step)
@@ -155,12 +158,15 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
              "grad_output must have value's dtype and shape (N, Lq, M*D)")
     meta = _capi.level_meta(spatial_shapes, level_start_index)
     aux = _aux_dtype(value)
-    grad_value = torch.empty(value.shape, dtype=aux, device=value.device)  # zero-filled by the library
+    # zero-filled by the library
+    grad_value = torch.empty(value.shape, dtype=aux, device=value.device) if _need_grad_value else None
     grad_loc = torch.empty_like(sampling_loc)
     grad_attw = torch.empty_like(attn_weight)
     if grad_loc.numel() == 0:  # no queries (or empty batch): nothing is sampled
-        return [grad_value.zero_(), grad_loc, grad_attw]
+        return [grad_value.zero_() if _need_grad_value else None, grad_loc, grad_attw]
     flags, ws = _flags, None
+    if not _need_grad_value:
+        flags |= _capi.FLAG_NO_GRAD_VALUE
     if is_deterministic() and value.dtype != torch.float64:
         flags |= _capi.FLAG_DETERMINISTIC
     if flags & _capi.FLAG_DETERMINISTIC:
@@ -170,7 +176,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
         rc = _BWD[sfx](
             _stream(value.device), grad_output.data_ptr(), value.data_ptr(), _dev_ptr(spatial_shapes),
             _dev_ptr(level_start_index), sampling_loc.data_ptr(), attn_weight.data_ptr(), n, s, m, d, nl, lq, npt,
-            grad_value.data_ptr(), grad_loc.data_ptr(), grad_attw.data_ptr(), opts)
+            grad_value.data_ptr() if _need_grad_value else None, grad_loc.data_ptr(), grad_attw.data_ptr(), opts)
     _capi.check(rc, "msda_backward_" + sfx)
     return [grad_value, grad_loc, grad_attw]
 

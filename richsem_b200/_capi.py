@@ -28,6 +28,8 @@ FLAG_AGGREGATE = 0x40
 FLAG_NO_WINDOW = 0x80
 FLAG_WINDOW_FWD = 0x100
 FLAG_LDG256 = 0x200
+FLAG_NO_GRAD_VALUE = 0x400
+FLAG_BWD_HALVES = 0x800
 MAX_LEVELS = 16
 
 _vp, _i, _i64p = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)

@@ -143,19 +143,20 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
                   const int64_t* start, const TA* loc, const TA* attw, int batch, int spatial_size,
                   int num_heads, int channels, int num_levels, int num_query, int num_point,
                   TA* gv, TA* gl, TA* ga, const msda_opts* opts) {
-  if (!grad_out || !value || !loc || !attw || !gv || !gl || !ga)
+  if (!grad_out || !value || !loc || !attw || !gl || !ga || (!gv && !(opt_flags(opts) & MSDA_FLAG_NO_GRAD_VALUE)))
     return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
   Problem pb;
   int rc = make_problem(s, shapes, start, batch, spatial_size, num_heads, channels, num_levels,
                         num_query, num_point, opts, &pb);
   if (rc != MSDA_OK) return rc;
   if (batch == 0) return MSDA_OK;
-  const bool det = (pb.flags & MSDA_FLAG_DETERMINISTIC) != 0;
+  const bool no_gv = (pb.flags & MSDA_FLAG_NO_GRAD_VALUE) != 0;  // value needs no gradient: gv may be NULL
+  const bool det = (pb.flags & MSDA_FLAG_DETERMINISTIC) != 0 && !no_gv;
   if (det && sizeof(TA) != 4)
     return fail(MSDA_ERR_UNSUPPORTED, "deterministic mode is implemented for fp32 / bf16 only");
   const size_t gv_bytes = (size_t)batch * spatial_size * num_heads * channels * sizeof(TA);
   // deterministic mode writes every grad_value row itself
-  if (!(pb.flags & MSDA_FLAG_GRAD_VALUE_PREZEROED) && !(det && num_query > 0)) {
+  if (!(pb.flags & MSDA_FLAG_GRAD_VALUE_PREZEROED) && !(det && num_query > 0) && !no_gv) {
     rc = check_cuda(cudaMemsetAsync(gv, 0, gv_bytes, s), "zero-fill of grad_value");
     if (rc != MSDA_OK) return rc;
   }
@@ -165,8 +166,18 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
                       fast_shape(sizeof(TV), channels, num_levels, num_point) && fits_int32(pb.d) &&
                       aligned(value, 16) && aligned(gv, 16) && aligned(loc, 16) && aligned(attw, 16) &&
                       aligned(grad_out, 16) && aligned(gl, 8);
+    if (fast && no_gv) return msda::bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
     if (fast) {
-      const bool window = !det && !msda::use_split(pb) && !(pb.flags & (MSDA_FLAG_NO_WINDOW | MSDA_FLAG_AGGREGATE));
+      // large problems: the fused window kernel (0.414 ms per bs=2 encoder layer).  MSDA_FLAG_BWD_HALVES runs
+      // the two halves of the backward as two kernels instead — gather + dot products for grad_sampling_loc /
+      // grad_attn_weight (0.200 ms), cell-sorted accumulation for grad_value (msda_d32_gv.cuh, 0.21 ms): no
+      // faster back to back (0.423 ms), kept because each half is useful alone (MSDA_FLAG_NO_GRAD_VALUE).
+      const bool large = !det && !msda::use_split(pb) && !(pb.flags & (MSDA_FLAG_NO_WINDOW | MSDA_FLAG_AGGREGATE));
+      if (large && (pb.flags & MSDA_FLAG_BWD_HALVES)) {
+        rc = msda::bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
+        return rc != MSDA_OK ? rc : msda::gradvalue_d32<TV>(s, pb, grad_out, loc, attw, gv);
+      }
+      const bool window = large;
       rc = window ? msda::bwd_d32_win<TV>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
            : det  ? msda::bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
                   : msda::bwd_d32<TV, true>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
@@ -180,7 +191,7 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
                                       opts ? opts->workspace_bytes : 0);
     }
   }
-  return msda::bwd_generic<TV, TA>(s, pb, true, grad_out, value, loc, attw, gv, gl, ga);
+  return msda::bwd_generic<TV, TA>(s, pb, !no_gv, grad_out, value, loc, attw, gv, gl, ga);
 }
 
 }  // namespace

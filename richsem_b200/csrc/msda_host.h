@@ -48,6 +48,10 @@ template <typename VT>
 int bwd_d32_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
                 const float* attw, float* gv, float* gl, float* ga);
 
+// grad_value alone, by cell-sorted accumulation (msda_d32_gv.cuh); pairs with bwd_d32<VT, false>.
+template <typename VT>
+int gradvalue_d32(cudaStream_t s, const Problem& pb, const VT* go, const float* loc, const float* attw, float* gv);
+
 // ---- msda_launch_other.cu: any-shape kernels, deterministic grad_value, index probe ----
 template <typename TV, typename TA>
 int fwd_generic(cudaStream_t s, const Problem& pb, const TV* value, const TA* loc, const TA* attw, TV* out);

@@ -1,6 +1,7 @@
 // msda_launch_win.cu — instantiates and launches the shared-memory window kernels (msda_d32_win.cuh).
 #include "msda_host.h"
 #include "msda_d32_win.cuh"
+#include "msda_d32_gv.cuh"
 
 namespace msda {
 namespace {
@@ -34,6 +35,19 @@ int launch_bwd_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* va
   return after_launch("msda_bwd_d32_win_kernel");
 }
 
+template <typename VT, int kL, int kM>
+int launch_gradvalue(cudaStream_t s, const Problem& pb, const VT* go, const float* loc, const float* attw, float* gv) {
+  using Cfg = GvCfg<kL>;
+  auto kern = msda_gradvalue_d32_kernel<VT, kL, kM>;
+  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_gradvalue_d32_kernel)");
+  const int tiles = (pb.order_len + kTileQ - 1) / kTileQ;
+  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
+  kern<<<grid, kWinThreads, Cfg::SMEM_BYTES, s>>>(go, loc, attw, gv, pb.order, pb.order_len, pb.lv,
+                                                  pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
+  return after_launch("msda_gradvalue_d32_kernel");
+}
+
 #define MSDA_SWITCH_L(L_, CALL)                                                              \
   switch (L_) {                                                                              \
     case 1: return CALL(1);                                                                  \
@@ -64,6 +78,17 @@ int bwd_d32_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value
   MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL
 }
+
+template <typename VT>
+int gradvalue_d32(cudaStream_t s, const Problem& pb, const VT* go, const float* loc, const float* attw, float* gv) {
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_gradvalue<VT, 4, 8>(s, pb, go, loc, attw, gv);
+#define CALL(L) launch_gradvalue<VT, L, 0>(s, pb, go, loc, attw, gv)
+  MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+}
+template int gradvalue_d32<float>(cudaStream_t, const Problem&, const float*, const float*, const float*, float*);
+template int gradvalue_d32<__nv_bfloat16>(cudaStream_t, const Problem&, const __nv_bfloat16*, const float*, const float*,
+                                          float*);
 
 template int fwd_d32_win<float>(cudaStream_t, const Problem&, const float*, const float*, const float*, float*);
 template int fwd_d32_win<__nv_bfloat16>(cudaStream_t, const Problem&, const __nv_bfloat16*, const float*,

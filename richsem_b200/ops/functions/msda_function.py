@@ -34,8 +34,10 @@ class MSDeformAttnFunction(Function):
         value, shapes, starts, locations, weights = ctx.saved_tensors
         # the kernels index grad_output as (N, Lq, M, D) densely (reference asserts the same,
         # ms_deform_attn_cuda.cu:98)
+        # (an input that needs no gradient — e.g. a detached / frozen `value` — skips its half of the work)
         g_value, g_loc, g_weight = _ext.ms_deform_attn_backward(
-            value, shapes, starts, locations, weights, grad_output.contiguous(), ctx.im2col_step)
-        if g_value.dtype != value.dtype:  # bf16 value: autograd wants the input's dtype
+            value, shapes, starts, locations, weights, grad_output.contiguous(), ctx.im2col_step,
+            _need_grad_value=ctx.needs_input_grad[0])
+        if g_value is not None and g_value.dtype != value.dtype:  # bf16 value: autograd wants the input's dtype
             g_value = g_value.to(value.dtype)
         return g_value, None, None, g_loc, g_weight, None

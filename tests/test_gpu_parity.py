@@ -40,7 +40,7 @@ def test_extension_is_loaded_from_the_tree():
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-@pytest.mark.parametrize("path", ["auto", "window", "tiled", "tiled256", "aggregate", "generic"])
+@pytest.mark.parametrize("path", ["auto", "halves", "window", "tiled", "tiled256", "aggregate", "generic"])
 def test_golden_forward_backward(case, path):
     """auto = what the library picks (warp-per-query "split" kernels at these sizes for D=32);
     window = the shared-memory window kernels used for large problems; tiled = their L1-gather
@@ -50,7 +50,8 @@ def test_golden_forward_backward(case, path):
     g = load_golden(case)
     f64 = g["value"].dtype == torch.float64
     v, shp, st, loc, w, go = _to_dev(g)
-    flags = {"auto": 0, "window": _capi.FLAG_NO_SPLIT | _capi.FLAG_WINDOW_FWD,
+    flags = {"auto": 0, "halves": _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_HALVES,
+             "window": _capi.FLAG_NO_SPLIT | _capi.FLAG_WINDOW_FWD,
              "tiled": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_AGGREGATE | _capi.FLAG_NO_WINDOW,
              "tiled256": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW | _capi.FLAG_LDG256,
              "aggregate": _capi.FLAG_AGGREGATE | _capi.FLAG_NO_WINDOW, "generic": _capi.FLAG_FORCE_GENERIC}[path]
@@ -136,15 +137,18 @@ def test_gradcheck_like_reference(channels):
     assert gradcheck(MSDeformAttnFunction.apply, (value, shapes, starts, loc, w, 2))
 
 
-@pytest.mark.parametrize("kind,n,lq,bflags", [("E", 1, None, 0), ("E", 1, None, "noagg"), ("U", 2, 600, 0),
-                                              ("U", 2, 600, "agg"), ("Dn", 2, 1100, 0), ("Dn", 2, 1100, "agg")])
+@pytest.mark.parametrize("kind,n,lq,bflags", [("E", 1, None, 0), ("E", 1, None, "halves"), ("E", 1, None, "tiled"),
+                                              ("U", 2, 3000, 0), ("U", 2, 3000, "halves"), ("U", 2, 600, "agg"),
+                                              ("Dn", 2, 1100, 0), ("Dn", 2, 1100, "agg")])
 def test_dino_shape_against_c_oracle(kind, n, lq, bflags, c_oracle):
     """Full DINO 4-scale R50 800x1333 pyramid (S=22223, M=8, D=32, L=4, P=4) against the C oracle.
-    Encoder ("E") takes the pre-aggregating backward by default; "agg" forces it on inputs without
-    locality (almost every point then falls back to direct reductions), "noagg" disables it."""
+    Large problems ("E"; "U" with 3000 queries: no locality, most levels fall back to direct reductions)
+    take the fused window backward by default; "halves" = gather kernel + cell-sorted grad_value kernel,
+    "tiled" = per-corner reductions, "agg" = the corner-sorted pre-aggregation."""
     from richsem_b200 import _capi, synthetic as syn
 
-    bflags = {0: 0, "agg": _capi.FLAG_AGGREGATE, "noagg": _capi.FLAG_NO_AGGREGATE}[bflags]
+    bflags = {0: 0, "agg": _capi.FLAG_AGGREGATE, "halves": _capi.FLAG_BWD_HALVES | _capi.FLAG_NO_SPLIT,
+              "tiled": _capi.FLAG_NO_WINDOW}[bflags]
     shapes = syn.level_shapes(800, 1333)
     i = syn.make_inputs(kind, n, shapes, "cuda:0", seed=21, lq=lq)
     out = _ext().ms_deform_attn_forward(i["value"], i["shapes"], i["starts"], i["loc"], i["attw"], 64)
@@ -249,11 +253,12 @@ def test_aggregated_backward_matches_plain_backward_bf16_and_five_levels():
         assert torch.equal(x[1], y[1]) and torch.equal(x[2], y[2])
 
 
-@pytest.mark.parametrize("path", ["auto", "window", "tiled", "generic"])
+@pytest.mark.parametrize("path", ["auto", "halves", "window", "tiled", "generic"])
 def test_bf16_value_variant(c_oracle, path):
     from richsem_b200 import _capi, synthetic as syn
 
-    flags = {"auto": 0, "window": _capi.FLAG_NO_SPLIT | _capi.FLAG_WINDOW_FWD,
+    flags = {"auto": 0, "halves": _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_HALVES,
+             "window": _capi.FLAG_NO_SPLIT | _capi.FLAG_WINDOW_FWD,
              "tiled": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW,
              "generic": _capi.FLAG_FORCE_GENERIC}[path]
     shapes = syn.level_shapes(800, 1333)
@@ -336,3 +341,20 @@ def test_module_forward_backward_matches_oracle_path():
     assert rel_err(out.detach().cpu(), want.detach()) < 1e-4
     assert rel_err(g_src.cpu(), src_c.grad) < 1e-3
     assert rel_err(g_off.cpu(), cpu.sampling_offsets.weight.grad) < 1e-3
+
+
+def test_value_without_grad_skips_grad_value_and_keeps_the_other_gradients():
+    from richsem_b200 import synthetic as syn
+    from richsem_b200.ops.functions import MSDeformAttnFunction
+
+    for shapes, lq in (([(40, 61), (20, 31), (10, 16), (5, 8)], None), ([(12, 17), (6, 9)], 50)):
+        i = syn.make_inputs("E" if lq is None else "U", 2, shapes, "cuda:0", seed=8, lq=lq)
+        got = {}
+        for need in (True, False):
+            v = i["value"].clone().requires_grad_(need)
+            loc = i["loc"].clone().requires_grad_(True)
+            w = i["attw"].clone().requires_grad_(True)
+            MSDeformAttnFunction.apply(v, i["shapes"], i["starts"], loc, w, 64).backward(i["grad_out"])
+            got[need] = (v.grad, loc.grad, w.grad)
+        assert got[False][0] is None and got[True][0] is not None
+        assert rel_err(got[False][1], got[True][1]) < 1e-6 and rel_err(got[False][2], got[True][2]) < 1e-6
