@@ -162,13 +162,23 @@ def run_reference(args):
         return
     steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
     hw, layers, bs, kind, lq, vdt = WORKLOADS[args.workload]
-    r = cpu_reference_run(steps, warmup, hw if kind == "E" else (800, 1333))
+    hw = hw if kind == "E" else (800, 1333)
+    r = cpu_reference_run(steps, warmup, hw)
+    from richsem_b200 import synthetic as syn
+
+    shapes = syn.level_shapes(*hw)
+    S = sum(h * w for h, w in shapes)
     line = {
         "metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "note": "CPU path of the reference op (grid_sample formulation), "
-                   "one encoder layer bs=1 per step, host cores only"},
+        "config": {"workload": args.workload, "image": f"{hw[0]}x{hw[1]}", "levels": shapes, "S": S, "Lq": S,
+                   "batch_per_gpu": bs, "layers_per_step": layers, "heads": 8, "head_dim": 32, "points": 4,
+                   "locations": "E", "grad_value_mode": "autograd of grid_sample",
+                   "parallelism": "rank 0 only, all host cores",
+                   "sample": "each step = ONE encoder layer at bs=1 of this workload (a bounded sample: the CPU path "
+                             "needs ~0.3 s per layer-image), reference op = grid_sample formulation "
+                             "(ms_deform_attn_core_pytorch restated in oracle/, bit-identical)"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -296,7 +306,7 @@ def run_b200(args):
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(steps=4, warmup=1)
+        r = cpu_reference_run(steps=12, warmup=2)
         cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     dom = "backward" if bwd_ms >= fwd_ms else "forward"
