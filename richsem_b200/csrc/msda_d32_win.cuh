@@ -552,24 +552,34 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
   }
   const size_t qm_pf = ((size_t)b * Lq + (qpf >= 0 ? qpf : 0)) * M + m;
   if (qpf >= 0 && dslot == 0) prefetch_l2(grad_out + qm_pf * 32);
-  // grad_out rows of the tile -> shared memory as fp32 (C floats per 16-byte global chunk)
-  for (int i = t; i < kTileQ * G; i += kWinThreads) {
+  // grad_out rows of the tile: loads issued now, parked in shared memory (as fp32) after the front end, so
+  // that their latency overlaps the decode's own loads instead of preceding them
+  constexpr int GO_ITERS = kTileQ * G / kWinThreads;
+  static_assert(kTileQ * G % kWinThreads == 0, "grad_out staging covers the tile in whole iterations");
+  float gvreg[GO_ITERS][C];
+#pragma unroll
+  for (int it = 0; it < GO_ITERS; ++it) {
+    const int i = t + it * kWinThreads;
     const int gql = i / G, gj = i % G;
     const int oslot = tile * kTileQ + gql;
     int gq = -1;
     if (oslot < order_len) gq = order ? order[oslot] : oslot;
-    float gv[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) gv[c] = 0.f;
-    if (gq >= 0) RT::load_stream(grad_out + (((size_t)b * Lq + gq) * M + m) * 32 + gj * C, gv);
-#pragma unroll
-    for (int c = 0; c < C; c += 4)
-      *reinterpret_cast<float4*>(go_s + gql * 32 + gj * C + c) = make_float4(gv[c], gv[c + 1], gv[c + 2], gv[c + 3]);
+    for (int c = 0; c < C; ++c) gvreg[it][c] = 0.f;
+    if (gq >= 0) RT::load_stream(grad_out + (((size_t)b * Lq + gq) * M + m) * 32 + gj * C, gvreg[it]);
   }
   WinAlloc<kL> wa;
   WinPoint pts[Cfg::NLV][4];
   int rank[Cfg::NLV][4];
   win_front_end<VT, kL, kWinPool, true>(value_img, loc, attw, dq, dqm, qpf, qm_pf, m, M, lv, pool, rec, bb, rowoff, hist, wa, pts, rank, tphase);
+#pragma unroll
+  for (int it = 0; it < GO_ITERS; ++it) {
+    const int i = t + it * kWinThreads;
+#pragma unroll
+    for (int c = 0; c < C; c += 4)
+      *reinterpret_cast<float4*>(go_s + (i / G) * 32 + (i % G) * C + c) =
+          make_float4(gvreg[it][c], gvreg[it][c + 1], gvreg[it][c + 2], gvreg[it][c + 3]);
+  }
   if (t < 2) rowoff[kWinPool + t] = -1;
   if (t >= 32 && t < 32 + kL) { lvf[t - 32] = (float)lv.W[t - 32]; lvf[8 + t - 32] = (float)lv.H[t - 32]; }
   __syncthreads();  // hist complete, records visible
