@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 constexpr int H = 100, W = 167, M = 8, BH = 16, BW = 16, ROWS = BH * BW;
+constexpr int BXW = 4;  // columns per small TMA box (mode 3)
 __device__ __forceinline__ unsigned lcg(unsigned& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
@@ -18,8 +19,8 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       : "memory");
 }
 template <int MODE>
-__global__ void __launch_bounds__(256) k(const float* __restrict__ value, const __grid_constant__ CUtensorMap tmap, float* out,
-                                         int iters, int gather) {
+__global__ void __launch_bounds__(256) k(const float* __restrict__ value, const __grid_constant__ CUtensorMap tmap,
+                                         const __grid_constant__ CUtensorMap tmap_small, float* out, int iters, int gather) {
   extern __shared__ __align__(128) unsigned char smraw[];
   float4* win = reinterpret_cast<float4*>(smraw);                   // staged window
   float4* res = reinterpret_cast<float4*>(smraw + ROWS * 128);      // resident window for the gather
@@ -55,6 +56,18 @@ __global__ void __launch_bounds__(256) k(const float* __restrict__ value, const 
                      "l"(src), "r"(smem_u32(&bar))
                      : "memory");
       }
+    } else if (MODE == 3) {
+      if (t == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(ROWS * 128) : "memory");
+      __syncthreads();
+      constexpr int CH = BW / BXW;
+      if (t < BH * CH) {
+        const int rh = t / CH, ch = t % CH;
+        asm volatile(
+            "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+                smem_u32(win + (rh * BW + ch * BXW) * 8)),
+            "l"(&tmap_small), "r"(0), "r"(m), "r"(w0 + ch * BXW), "r"(h0 + rh), "r"(b), "r"(smem_u32(&bar))
+            : "memory");
+      }
     } else {
       if (t == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(ROWS * 128) : "memory");
@@ -81,13 +94,13 @@ __global__ void __launch_bounds__(256) k(const float* __restrict__ value, const 
 }
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-template <int MODE> void run(const char* name, const float* value, const CUtensorMap& tm, int bps, int iters, int gather) {
+template <int MODE> void run(const char* name, const float* value, const CUtensorMap& tm, const CUtensorMap& tms, int bps, int iters, int gather) {
   float* out; cudaMalloc(&out, 16);
   size_t sm = 2 * ROWS * 128;
   cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-  k<MODE><<<148 * bps, 256, sm>>>(value, tm, out, 10, gather); cudaDeviceSynchronize();
-  cudaEventRecord(a); k<MODE><<<148 * bps, 256, sm>>>(value, tm, out, iters, gather); cudaEventRecord(b); cudaEventSynchronize(b);
+  k<MODE><<<148 * bps, 256, sm>>>(value, tm, tms, out, 10, gather); cudaDeviceSynchronize();
+  cudaEventRecord(a); k<MODE><<<148 * bps, 256, sm>>>(value, tm, tms, out, iters, gather); cudaEventRecord(b); cudaEventSynchronize(b);
   float ms; cudaEventElapsedTime(&ms, a, b);
   int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
   const double cyc = ms * 1e-3 * clk * 1e3 / (iters * bps);   // cycles per window per SM-slot
@@ -105,12 +118,16 @@ int main() {
   cuuint32_t box[5] = {32, 1, BW, BH, 1}, es[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, value, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  printf("encode: %d\n", (int)r);
+  CUtensorMap tms;
+  cuuint32_t box_s[5] = {32, 1, BXW, 1, 1};
+  CUresult r2 = enc(&tms, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, value, dims, strides, box_s, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  printf("encode: %d %d\n", (int)r, (int)r2);
   for (int bps = 1; bps <= 2; ++bps)
     for (int gather : {0, 64, 128}) {
-      run<0>("cp.async 16 B", value, tm, bps, 2000, gather);
-      run<1>("bulk 1-D 128 B per row", value, tm, bps, 2000, gather);
-      run<2>("tensor 5-D box", value, tm, bps, 2000, gather);
+      run<0>("cp.async 16 B", value, tm, tms, bps, 2000, gather);
+      run<2>("tensor 5-D box 16x16", value, tm, tms, bps, 2000, gather);
+      run<3>("tensor 5-D boxes 1x4 (64 ops)", value, tm, tms, bps, 2000, gather);
     }
   return 0;
 }
