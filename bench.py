@@ -59,7 +59,6 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="encoder6", choices=sorted(WORKLOADS))
     ap.add_argument("--deterministic", action="store_true")
-    ap.add_argument("--aggregate", action="store_true", help="backward: pre-aggregate grad_value on chip (opt-in)")
     ap.add_argument("--lib-flags", type=lambda x: int(x, 0), default=0,
                     help="extra MSDA_FLAG_* bits for forward and backward (kernel-selection experiments)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -239,8 +238,6 @@ def run_b200(args):
     shp, st = sets[0]["shapes"], sets[0]["starts"]
     queries_per_step = layers * bs * Lq
     flags = _capi.FLAG_DETERMINISTIC if args.deterministic else 0
-    if args.aggregate:
-        flags |= _capi.FLAG_AGGREGATE
     flags |= args.lib_flags
     vb = 2 if vdt == "bf16" else 4
     fwd_bytes, bwd_bytes = syn.algorithmic_bytes(bs, S, Lq, value_bytes=vb, out_bytes=vb)
@@ -324,7 +321,7 @@ def run_b200(args):
         "vs_baseline": None, "dtype": vdt, "data": "synthetic",
         "config": {"workload": args.workload, "image": f"{hw[0]}x{hw[1]}", "levels": shapes, "S": S, "Lq": Lq,
                    "batch_per_gpu": bs, "layers_per_step": layers, "heads": 8, "head_dim": 32, "points": 4,
-                   "locations": kind, "grad_value_mode": "deterministic" if args.deterministic else ("atomic, pre-aggregated on chip" if args.aggregate else "atomic"),
+                   "locations": kind, "grad_value_mode": "deterministic" if args.deterministic else "atomic (merged on chip per window cell, then fp32 L2 reductions)",
                    "parallelism": f"batch-sharded x{world}, no collective in the op",
                    "l2_policy": f"{layers} distinct input sets per step ({in_bytes / 1e6:.0f} MB of inputs) "
                                 "larger than the 126 MB L2; no explicit flush"},

@@ -68,8 +68,6 @@ extern "C" {
 #define MSDA_FLAG_FORCE_GENERIC 0x4u          /* bypass the D=32 fast kernels (testing)                             */
 #define MSDA_FLAG_COORDS_FMA 0x10u             /* pixel coordinate = fma(loc, size, -0.5): what nvcc -fmad=true makes of
                                                  cuh:285-286, i.e. the compiled reference; default is mul-then-sub  */
-#define MSDA_FLAG_NO_AGGREGATE 0x20u           /* backward: never pre-aggregate grad_value on chip (comparison)    */
-#define MSDA_FLAG_AGGREGATE 0x40u              /* backward: pre-aggregate even without a query_order (testing)     */
 #define MSDA_FLAG_NO_WINDOW 0x80u              /* backward: keep the L1-gather tiled kernel instead of the shared-memory window kernel */
 #define MSDA_FLAG_BWD_HALVES 0x800u            /* backward: gather kernel + cell-sorted grad_value kernel instead of the fused window kernel */
 #define MSDA_FLAG_NO_GRAD_VALUE 0x400u         /* backward: value needs no gradient; grad_value is not touched and may be NULL   */

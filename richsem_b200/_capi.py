@@ -23,8 +23,6 @@ FLAG_GRAD_VALUE_PREZEROED = 0x2
 FLAG_FORCE_GENERIC = 0x4
 FLAG_NO_SPLIT = 0x8
 FLAG_COORDS_FMA = 0x10
-FLAG_NO_AGGREGATE = 0x20
-FLAG_AGGREGATE = 0x40
 FLAG_NO_WINDOW = 0x80
 FLAG_WINDOW_FWD = 0x100
 FLAG_LDG256 = 0x200
@@ -167,7 +165,7 @@ def build_patch_order(shapes, starts, pad=False):
                neighbouring patches.
     pad=True:  every patch occupies exactly 64 entries, missing pixels are -1 (skipped by the
                kernels), so that one block = one patch everywhere (tighter windows for the L1 and
-               for the on-chip grad_value aggregation, at the price of some idle lane groups)."""
+               for the on-chip grad_value merging of the window backward, at the price of some idle lane groups)."""
     import numpy as np
 
     parts = []

@@ -172,7 +172,7 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
       // the two halves of the backward as two kernels instead — gather + dot products for grad_sampling_loc /
       // grad_attn_weight (0.200 ms), cell-sorted accumulation for grad_value (msda_d32_gv.cuh, 0.21 ms): no
       // faster back to back (0.423 ms), kept because each half is useful alone (MSDA_FLAG_NO_GRAD_VALUE).
-      const bool large = !det && !msda::use_split(pb) && !(pb.flags & (MSDA_FLAG_NO_WINDOW | MSDA_FLAG_AGGREGATE));
+      const bool large = !det && !msda::use_split(pb) && !(pb.flags & MSDA_FLAG_NO_WINDOW);
       if (large && (pb.flags & MSDA_FLAG_BWD_HALVES)) {
         rc = msda::bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
         return rc != MSDA_OK ? rc : msda::gradvalue_d32<TV>(s, pb, grad_out, loc, attw, gv);

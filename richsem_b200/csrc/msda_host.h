@@ -34,8 +34,7 @@ inline bool use_split(const Problem& pb) {
 }
 
 // ---- head_dim 32, 4 points, 1..6 levels; VT = float | __nv_bfloat16 (explicitly instantiated) ----
-// msda_launch_d32.cu: L1-gather kernels (tiled for large problems, split for small ones, opt-in
-// pre-aggregating backward).
+// msda_launch_d32.cu: L1-gather kernels (tiled for large problems, split for small ones).
 template <typename VT>
 int fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const float* loc, const float* attw, VT* out);
 template <typename VT, bool kScatter>

@@ -1,8 +1,7 @@
-// msda_launch_d32.cu — instantiates and launches the L1-gather D=32 kernels (msda_d32.cuh,
-// msda_d32_agg.cuh): tiled, split and the opt-in pre-aggregating backward.
+// msda_launch_d32.cu — instantiates and launches the L1-gather D=32 kernels (msda_d32.cuh):
+// tiled and split.
 #include "msda_host.h"
 #include "msda_d32.cuh"
-#include "msda_d32_agg.cuh"
 
 namespace msda {
 namespace {
@@ -61,29 +60,6 @@ int launch_bwd_split(cudaStream_t s, const Problem& pb, const VT* grad_out, cons
   return after_launch("msda_bwd_d32_split_kernel");
 }
 
-template <typename VT, int kL, int kM>
-int launch_bwd_agg(cudaStream_t s, const Problem& pb, const VT* grad_out, const VT* value,
-                   const float* loc, const float* attw, float* gv, float* gl, float* ga) {
-  using Cfg = msda::AggCfg<kL>;
-  auto kern = msda::msda_bwd_d32_agg_kernel<VT, kL, kM>;
-  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-  if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_bwd_d32_agg_kernel)");
-  const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
-  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
-  kern<<<grid, msda::kAggThreads, Cfg::SMEM_BYTES, s>>>(grad_out, value, loc, attw, gv, gl, ga, pb.order,
-                                                        pb.order_len, pb.lv, pb.d.spatial_size,
-                                                        pb.d.num_heads, pb.d.num_query);
-  return after_launch("msda_bwd_d32_agg_kernel");
-}
-
-// On-chip pre-aggregation of grad_value (msda_d32_agg.cuh) cuts the L2 reductions 8.7x but, as
-// measured on B200 (profiles/r1_bwd_agg.md), its counting sort makes it latency-bound: 0.62 ms
-// against 0.47 ms for the plain kernel at the headline shape.  It stays opt-in.
-inline bool use_aggregate(const Problem& pb) {
-  if (pb.flags & MSDA_FLAG_NO_AGGREGATE) return false;
-  return (pb.flags & MSDA_FLAG_AGGREGATE) != 0;
-}
-
 #define MSDA_SWITCH_L(L_, CALL)                                                              \
   switch (L_) {                                                                              \
     case 1: return CALL(1);                                                                  \
@@ -127,12 +103,6 @@ int fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const float* loc
 template <typename VT, bool kScatter>
 int bwd_d32(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
             const float* attw, float* gv, float* gl, float* ga) {
-  if (kScatter && use_aggregate(pb) && (!use_split(pb) || (pb.flags & MSDA_FLAG_AGGREGATE))) {
-    if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_bwd_agg<VT, 4, 8>(s, pb, go, value, loc, attw, gv, gl, ga);
-#define CALL(L) launch_bwd_agg<VT, L, 0>(s, pb, go, value, loc, attw, gv, gl, ga)
-    MSDA_SWITCH_L(pb.d.num_levels, CALL)
-#undef CALL
-  }
   if (use_split(pb)) {
     if (pb.d.num_heads == 8 && pb.d.num_levels == 4)
       return launch_bwd_split<VT, 4, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);

@@ -40,7 +40,7 @@ def test_extension_is_loaded_from_the_tree():
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-@pytest.mark.parametrize("path", ["auto", "halves", "window", "tiled", "tiled256", "aggregate", "generic"])
+@pytest.mark.parametrize("path", ["auto", "halves", "window", "tiled", "tiled256", "generic"])
 def test_golden_forward_backward(case, path):
     """auto = what the library picks (warp-per-query "split" kernels at these sizes for D=32);
     window = the shared-memory window kernels used for large problems; tiled = their L1-gather
@@ -52,9 +52,9 @@ def test_golden_forward_backward(case, path):
     v, shp, st, loc, w, go = _to_dev(g)
     flags = {"auto": 0, "halves": _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_HALVES,
              "window": _capi.FLAG_NO_SPLIT | _capi.FLAG_WINDOW_FWD,
-             "tiled": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_AGGREGATE | _capi.FLAG_NO_WINDOW,
+             "tiled": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW,
              "tiled256": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW | _capi.FLAG_LDG256,
-             "aggregate": _capi.FLAG_AGGREGATE | _capi.FLAG_NO_WINDOW, "generic": _capi.FLAG_FORCE_GENERIC}[path]
+             "generic": _capi.FLAG_FORCE_GENERIC}[path]
     out = _ext().ms_deform_attn_forward(v, shp, st, loc, w, 64, _flags=flags)
     gv, gl, ga = _ext().ms_deform_attn_backward(v, shp, st, loc, w, go, 64, _flags=flags)
     ft, bt = (1e-12, 1e-11) if f64 else (FWD_TOL, BWD_TOL)
@@ -138,16 +138,16 @@ def test_gradcheck_like_reference(channels):
 
 
 @pytest.mark.parametrize("kind,n,lq,bflags", [("E", 1, None, 0), ("E", 1, None, "halves"), ("E", 1, None, "tiled"),
-                                              ("U", 2, 3000, 0), ("U", 2, 3000, "halves"), ("U", 2, 600, "agg"),
-                                              ("Dn", 2, 1100, 0), ("Dn", 2, 1100, "agg")])
+                                              ("U", 2, 3000, 0), ("U", 2, 3000, "halves"), ("U", 2, 3000, "window"),
+                                              ("Dn", 2, 1100, 0), ("Dn", 2, 1100, "window")])
 def test_dino_shape_against_c_oracle(kind, n, lq, bflags, c_oracle):
     """Full DINO 4-scale R50 800x1333 pyramid (S=22223, M=8, D=32, L=4, P=4) against the C oracle.
     Large problems ("E"; "U" with 3000 queries: no locality, most levels fall back to direct reductions)
     take the fused window backward by default; "halves" = gather kernel + cell-sorted grad_value kernel,
-    "tiled" = per-corner reductions, "agg" = the corner-sorted pre-aggregation."""
+    "tiled" = per-corner reductions, "window" = the fused window kernel forced on small / non-local inputs."""
     from richsem_b200 import _capi, synthetic as syn
 
-    bflags = {0: 0, "agg": _capi.FLAG_AGGREGATE, "halves": _capi.FLAG_BWD_HALVES | _capi.FLAG_NO_SPLIT,
+    bflags = {0: 0, "window": _capi.FLAG_NO_SPLIT, "halves": _capi.FLAG_BWD_HALVES | _capi.FLAG_NO_SPLIT,
               "tiled": _capi.FLAG_NO_WINDOW}[bflags]
     shapes = syn.level_shapes(800, 1333)
     i = syn.make_inputs(kind, n, shapes, "cuda:0", seed=21, lq=lq)
@@ -175,7 +175,7 @@ def test_query_order_does_not_change_results(monkeypatch):
     from richsem_b200 import _capi
 
     args = (i["value"], i["shapes"], i["starts"], i["loc"], i["attw"])
-    nosplit = _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_AGGREGATE
+    nosplit = _capi.FLAG_NO_SPLIT
     a = _ext().ms_deform_attn_forward(*args, 64, _flags=nosplit)
     ga = _ext().ms_deform_attn_backward(*args, i["grad_out"], 64, _flags=nosplit)
     monkeypatch.setenv("MSDA_B200_QUERY_ORDER", "natural")
@@ -237,9 +237,9 @@ def test_deterministic_mode_is_bitwise_reproducible_and_close_to_atomic():
     assert rel_err(e1[0], e3[0]) < BWD_TOL
 
 
-def test_aggregated_backward_matches_plain_backward_bf16_and_five_levels():
-    """Pre-aggregating backward vs the plain atomic one: bf16 value, and a 5-level pyramid (kL=5 decodes
-    two levels in some threads)."""
+def test_window_backward_matches_tiled_backward_bf16_and_five_levels():
+    """Window backward vs the plain atomic one: bf16 value, and a 5-level pyramid (kL=5 decodes two
+    levels in some threads)."""
     from richsem_b200 import _capi, synthetic as syn
 
     b = _ext().ms_deform_attn_backward
@@ -247,10 +247,11 @@ def test_aggregated_backward_matches_plain_backward_bf16_and_five_levels():
                           ([(33, 47), (17, 24), (9, 12), (5, 6), (3, 3)], torch.float32)):
         i = syn.make_inputs("E", 2, shapes, "cuda:0", seed=4, dtype=dtype)
         args = (i["value"], i["shapes"], i["starts"], i["loc"], i["attw"], i["grad_out"], 64)
-        x = b(*args, _flags=_capi.FLAG_AGGREGATE | _capi.FLAG_NO_SPLIT)
-        y = b(*args, _flags=_capi.FLAG_NO_AGGREGATE | _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW)
-        assert rel_err(x[0], y[0]) < 1e-5
-        assert torch.equal(x[1], y[1]) and torch.equal(x[2], y[2])
+        y = b(*args, _flags=_capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW)
+        for fl in (_capi.FLAG_NO_SPLIT, _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_HALVES):
+            x = b(*args, _flags=fl)
+            assert rel_err(x[0], y[0]) < 1e-5
+            assert rel_err(x[1], y[1]) < 1e-5 and rel_err(x[2], y[2]) < 1e-5
 
 
 @pytest.mark.parametrize("path", ["auto", "halves", "window", "tiled", "generic"])
