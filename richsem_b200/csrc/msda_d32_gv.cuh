@@ -30,13 +30,13 @@ struct GvCfg {
   static constexpr int LP = kL * 4;
   static constexpr int NLV = (kL + 3) / 4;
   static constexpr int REC_STRIDE = LP + 1;
-  static constexpr int REC_BYTES = kTileQ * REC_STRIDE * 16;
-  static constexpr int GO_BYTES = kTileQ * 32 * 4;
+  static constexpr int REC_BYTES = kWinTileQ * REC_STRIDE * 16;
+  static constexpr int GO_BYTES = kWinTileQ * 32 * 4;
   static constexpr int HIST_N = ((kGvCells + kWinThreads - 1) / kWinThreads) * kWinThreads;
   static constexpr int SPT = HIST_N / kWinThreads;
   static constexpr int HIST_BYTES = (HIST_N + 4) * 4;
   static constexpr int ROWOFF_BYTES = (kGvCells + 4) * 4;
-  static constexpr int SORTED_BYTES = ((kTileQ * LP * 2 + 15) / 16) * 16 + 16;
+  static constexpr int SORTED_BYTES = ((kWinTileQ * LP * 2 + 15) / 16) * 16 + 16;
   static constexpr int OFF_GO = REC_BYTES;
   static constexpr int OFF_HIST = OFF_GO + GO_BYTES;
   static constexpr int OFF_ROWOFF = OFF_HIST + HIST_BYTES;
@@ -62,8 +62,8 @@ msda_gradvalue_d32_kernel(const VT* __restrict__ grad_out, const float* __restri
   int* hist = reinterpret_cast<int*>(smraw + Cfg::OFF_HIST);  // counts, then exclusive offsets
   int* rowoff = reinterpret_cast<int*>(smraw + Cfg::OFF_ROWOFF);
   unsigned short* sorted = reinterpret_cast<unsigned short*>(smraw + Cfg::OFF_SORTED);
-  int* misc = reinterpret_cast<int*>(smraw + Cfg::OFF_MISC);  // [0,8) warp totals [8] total [16,48) bounding boxes
-  int* bb = misc + 16;
+  int* misc = reinterpret_cast<int*>(smraw + Cfg::OFF_MISC);  // [0,16) warp totals [16] total [32,64) bounding boxes
+  int* bb = misc + 32;
 
   const int M = kM ? kM : M_rt;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -72,10 +72,10 @@ msda_gradvalue_d32_kernel(const VT* __restrict__ grad_out, const float* __restri
   const size_t img = (size_t)b * S * M32;
 
   // ---- decode + bounding boxes: thread = (level slot, query), level warp-uniform -------------------
-  const int dql = t & (kTileQ - 1), dslot = t / kTileQ;
+  const int dql = t & (kWinTileQ - 1), dslot = t / kWinTileQ;
   int dq = -1;
   {
-    const int oslot = tile * kTileQ + dql;
+    const int oslot = tile * kWinTileQ + dql;
     if (oslot < order_len) dq = order ? order[oslot] : oslot;
   }
   const size_t dqm = ((size_t)b * Lq + (dq >= 0 ? dq : 0)) * M + m;
@@ -83,9 +83,9 @@ msda_gradvalue_d32_kernel(const VT* __restrict__ grad_out, const float* __restri
 #pragma unroll
   for (int k = 0; k < Cfg::SPT; ++k) hist[t + k * kWinThreads] = 0;
   // grad_out rows of the tile -> shared memory as fp32
-  for (int i = t; i < kTileQ * GG; i += kWinThreads) {
+  for (int i = t; i < kWinTileQ * GG; i += kWinThreads) {
     const int gql = i / GG, gj = i % GG;
-    const int oslot = tile * kTileQ + gql;
+    const int oslot = tile * kWinTileQ + gql;
     int gq = -1;
     if (oslot < order_len) gq = order ? order[oslot] : oslot;
     float gv[GC];
@@ -175,7 +175,7 @@ msda_gradvalue_d32_kernel(const VT* __restrict__ grad_out, const float* __restri
     for (int w = 0; w < warp; ++w) run += misc[w];
 #pragma unroll
     for (int k = 0; k < Cfg::SPT; ++k) { hist[t * Cfg::SPT + k] = run; run += v[k]; }
-    if (t == kWinThreads - 1) misc[8] = run;
+    if (t == kWinThreads - 1) misc[16] = run;
     __syncthreads();
   }
 #pragma unroll
@@ -202,7 +202,7 @@ msda_gradvalue_d32_kernel(const VT* __restrict__ grad_out, const float* __restri
     float* gvalue_b = grad_value + img + oB / 4;
     const unsigned char* go_a = reinterpret_cast<const unsigned char*>(go_s) + oA;
     const unsigned char* go_b = reinterpret_cast<const unsigned char*>(go_s) + oB;
-    const int total = misc[8];
+    const int total = misc[16];
     const int chunk = (((total + SNG - 1) / SNG) + 3) & ~3;
     const int gi = warp * 8 + sg;
     const int i0 = min(total, gi * chunk), i1 = min(total, i0 + chunk);
@@ -241,7 +241,7 @@ msda_gradvalue_d32_kernel(const VT* __restrict__ grad_out, const float* __restri
           }
           const int code = __float_as_int(r.x);
           const int row0 = code & 0xffff, row1 = code >> 16;
-          WIN_CHECK(sid < kTileQ * LP && row0 >= cur0 && row1 + 1 < kGvCells && row1 > row0);
+          WIN_CHECK(sid < kWinTileQ * LP && row0 >= cur0 && row1 + 1 < kGvCells && row1 > row0);
           if (row0 != cur0) {
             const bool adj = (row0 == cur0 + 1);
             if (cur0 >= 0) {
@@ -291,7 +291,7 @@ msda_gradvalue_d32_kernel(const VT* __restrict__ grad_out, const float* __restri
   if (!all_cells) {
     const int g = lane >> 3, j = lane & 7;  // 8 lanes x float4 per fp32 row
     float* gvalue_j = grad_value + img + j * 4;
-    for (int ql = warp * 4 + g; ql < kTileQ; ql += kWinThreads / 8) {
+    for (int ql = warp * 4 + g; ql < kWinTileQ; ql += kWinThreads / 8) {
       const float4 go = *reinterpret_cast<const float4*>(go_s + ql * 32 + j * 4);
 #pragma unroll
       for (int l = 0; l < kL; ++l) {

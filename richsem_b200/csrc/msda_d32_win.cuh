@@ -40,7 +40,14 @@
 
 namespace msda {
 
-constexpr int kWinThreads = 256;
+// Queries per block of the window kernels; 4 threads per query (one per level slot).  The host's padded
+// 8x8-patch order serves 64 (one patch) as well as 32 (the upper / lower 8x4 half of a patch).
+#ifndef MSDA_WIN_TILE
+#define MSDA_WIN_TILE 64
+#endif
+constexpr int kWinTileQ = MSDA_WIN_TILE;
+constexpr int kWinThreads = 4 * kWinTileQ;
+static_assert(kWinTileQ == 32 || kWinTileQ == 64 || kWinTileQ == 128, "window kernels: 32, 64 or 128 queries per block");
 // Rows of the window pool.  Forward: 448 rows = 75 KB per block with the records, three blocks per SM.
 // Backward: 448 rows = 89 KB with the sort structures, two blocks per SM (128 registers per thread);
 // measured per bs=2 encoder layer: 256 rows 0.464 ms, 320 0.442, 384 0.425, 448 0.414, 592 0.434.
@@ -86,7 +93,7 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void* src, int sr
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // How many tiles ahead a block prefetches sampling locations / weights / grad_out (~ one wave of blocks:
 // 148 SMs x 2..3 blocks / 8 heads).
-constexpr int kWinPrefetchTiles = 48;
+constexpr int kWinPrefetchTiles = 48 * 64 / kWinTileQ;
 
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
@@ -118,24 +125,24 @@ struct WinCfg {
   static constexpr int REC_STRIDE = LP + 1;           // float4 per query (+1: bank skew)
   static constexpr int ROWB = WinRow<VT>::ROWB;
   static constexpr int POOL_BYTES = (kWinPool + 2) * ROWB;  // + two all-zero rows for skipped samples
-  static constexpr int REC_BYTES = kTileQ * REC_STRIDE * 16;
+  static constexpr int REC_BYTES = kWinTileQ * REC_STRIDE * 16;
   static constexpr int BB_BYTES = 32 * 4;
   static constexpr int FWD_SMEM = POOL_BYTES + REC_BYTES + BB_BYTES;
   // backward extras
   static constexpr int HIST_N = ((kWinPool + kWinThreads - 1) / kWinThreads) * kWinThreads;  // padded for the scan
   static constexpr int SPT = HIST_N / kWinThreads;
-  static constexpr int GO_BYTES = kTileQ * 32 * 4;            // grad_out rows of the tile, fp32
+  static constexpr int GO_BYTES = kWinTileQ * 32 * 4;            // grad_out rows of the tile, fp32
   static constexpr int HIST_BYTES = (HIST_N + 4) * 4;         // counts -> offsets (+ total)
   static constexpr int ROWOFF_BYTES = (kWinPool + 2) * 4;
-  static constexpr int SORTED_BYTES = ((kTileQ * LP * 2 + 15) / 16) * 16 + 16;
+  static constexpr int SORTED_BYTES = ((kWinTileQ * LP * 2 + 15) / 16) * 16 + 16;
   static constexpr int OFF_GO = POOL_BYTES + REC_BYTES + BB_BYTES;
   static constexpr int OFF_HIST = OFF_GO + GO_BYTES;
   static constexpr int OFF_ROWOFF = OFF_HIST + HIST_BYTES;
   static constexpr int OFF_SORTED = OFF_ROWOFF + ROWOFF_BYTES;
-  static constexpr int BWD_SMEM = OFF_SORTED + SORTED_BYTES + 128;
+  static constexpr int BWD_SMEM = OFF_SORTED + SORTED_BYTES + 192;
   static_assert(kL <= 8, "per-level state is kept in 8-entry arrays");
   static_assert(kWinPool + 2 < 32768, "two pool rows are packed in one record word");
-  static_assert(kTileQ * LP < 65536, "sample ids are stored as 16-bit");
+  static_assert(kWinTileQ * LP < 65536, "sample ids are stored as 16-bit");
 };
 
 // Per-level window decision, computed identically by every thread from the block's bounding boxes.
@@ -262,7 +269,7 @@ __device__ __forceinline__ void win_front_end(const VT* __restrict__ value_img, 
                                               int (&rank)[WinCfg<VT, kL, kWinPool>::NLV][4], long long& tph) {
   using Cfg = WinCfg<VT, kL, kWinPool>;
   const int t = threadIdx.x, lane = t & 31;
-  const int ql = t & (kTileQ - 1), slot = t / kTileQ;
+  const int ql = t & (kWinTileQ - 1), slot = t / kWinTileQ;
   if (t < 32) bb[t] = (t & 8) ? INT_MIN : INT_MAX;  // [0,8) hmin [8,16) hmax [16,24) wmin [24,32) wmax
   if (t >= 32 && t < 32 + 2 * Cfg::ROWB / 16)
     reinterpret_cast<uint4*>(pool + kWinPool * Cfg::ROWB)[t - 32] = make_uint4(0u, 0u, 0u, 0u);
@@ -335,8 +342,8 @@ msda_fwd_d32_win_kernel(const VT* __restrict__ value, const float* __restrict__ 
   using RT = RowTraits<VT>;
   using WR = WinRow<VT>;
   constexpr int LP = Cfg::LP, G = RT::G, C = RT::C, GPW = 32 / G, ROWB = Cfg::ROWB;
-  constexpr int QPP = (kWinThreads / 32) * GPW, PASSES = kTileQ / QPP;
-  static_assert(kTileQ * 4 == kWinThreads, "decode maps 4 threads to a query");
+  constexpr int QPP = (kWinThreads / 32) * GPW, PASSES = kWinTileQ / QPP;
+  static_assert(kWinTileQ * 4 == kWinThreads, "decode maps 4 threads to a query");
 
   extern __shared__ __align__(128) unsigned char smraw[];
   unsigned char* pool = smraw;
@@ -355,11 +362,11 @@ msda_fwd_d32_win_kernel(const VT* __restrict__ value, const float* __restrict__ 
   WinAlloc<kL> wa;
   {
     int q = -1;
-    const int oslot = tile * kTileQ + (t & (kTileQ - 1));
+    const int oslot = tile * kWinTileQ + (t & (kWinTileQ - 1));
     if (oslot < order_len) q = order ? order[oslot] : oslot;
     const size_t qm = ((size_t)b * Lq + (q >= 0 ? q : 0)) * M + m;
     int qpf = -1;
-    const int pslot = oslot + kWinPrefetchTiles * kTileQ;
+    const int pslot = oslot + kWinPrefetchTiles * kWinTileQ;
     if (pslot < order_len) qpf = order ? order[pslot] : pslot;
     const size_t qm_pf = ((size_t)b * Lq + (qpf >= 0 ? qpf : 0)) * M + m;
     WinPoint pts[Cfg::NLV][4];
@@ -381,7 +388,7 @@ msda_fwd_d32_win_kernel(const VT* __restrict__ value, const float* __restrict__ 
 #pragma unroll 1
   for (int pass = 0; pass < PASSES; ++pass) {
     const int ql = pass * QPP + warp * GPW + g;
-    const int oslot = tile * kTileQ + ql;
+    const int oslot = tile * kWinTileQ + ql;
     int q = -1;
     if (oslot < order_len) q = order ? order[oslot] : oslot;
     if (q < 0) continue;
@@ -515,7 +522,7 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
   using WR = WinRow<VT>;
   constexpr int LP = Cfg::LP, G = RT::G, C = RT::C, GPW = 32 / G, ROWB = Cfg::ROWB;
   constexpr int NG = (kWinThreads / 32) * GPW;  // lane groups per block
-  static_assert(kTileQ * 4 == kWinThreads, "decode maps 4 threads to a query");
+  static_assert(kWinTileQ * 4 == kWinThreads, "decode maps 4 threads to a query");
 
   extern __shared__ __align__(128) unsigned char smraw[];
   unsigned char* pool = smraw;
@@ -525,8 +532,8 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
   int* hist = reinterpret_cast<int*>(smraw + Cfg::OFF_HIST);       // counts, then exclusive offsets
   int* rowoff = reinterpret_cast<int*>(smraw + Cfg::OFF_ROWOFF);
   unsigned short* sorted = reinterpret_cast<unsigned short*>(smraw + Cfg::OFF_SORTED);
-  int* misc = reinterpret_cast<int*>(smraw + Cfg::OFF_SORTED + Cfg::SORTED_BYTES);  // [0,8) warp totals [8] total
-  float* lvf = reinterpret_cast<float*>(misc + 16);  // [0,8) (float)W_l  [8,16) (float)H_l
+  int* misc = reinterpret_cast<int*>(smraw + Cfg::OFF_SORTED + Cfg::SORTED_BYTES);  // [0,16) warp totals [16] total
+  float* lvf = reinterpret_cast<float*>(misc + 32);  // [0,8) (float)W_l  [8,16) (float)H_l
 
   const int M = kM ? kM : M_rt;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -538,30 +545,30 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
   // ---- front end -------------------------------------------------------------------------------
   long long tphase = clock64();
   (void)tphase;
-  const int dql = t & (kTileQ - 1), dslot = t / kTileQ;
+  const int dql = t & (kWinTileQ - 1), dslot = t / kWinTileQ;
   int dq = -1;
   {
-    const int oslot = tile * kTileQ + dql;
+    const int oslot = tile * kWinTileQ + dql;
     if (oslot < order_len) dq = order ? order[oslot] : oslot;
   }
   const size_t dqm = ((size_t)b * Lq + (dq >= 0 ? dq : 0)) * M + m;
   int qpf = -1;
   {
-    const int pslot = (tile + kWinPrefetchTiles) * kTileQ + dql;
+    const int pslot = (tile + kWinPrefetchTiles) * kWinTileQ + dql;
     if (pslot < order_len) qpf = order ? order[pslot] : pslot;
   }
   const size_t qm_pf = ((size_t)b * Lq + (qpf >= 0 ? qpf : 0)) * M + m;
   if (qpf >= 0 && dslot == 0) prefetch_l2(grad_out + qm_pf * 32);
   // grad_out rows of the tile: loads issued now, parked in shared memory (as fp32) after the front end, so
   // that their latency overlaps the decode's own loads instead of preceding them
-  constexpr int GO_ITERS = kTileQ * G / kWinThreads;
-  static_assert(kTileQ * G % kWinThreads == 0, "grad_out staging covers the tile in whole iterations");
+  constexpr int GO_ITERS = kWinTileQ * G / kWinThreads;
+  static_assert(kWinTileQ * G % kWinThreads == 0, "grad_out staging covers the tile in whole iterations");
   float gvreg[GO_ITERS][C];
 #pragma unroll
   for (int it = 0; it < GO_ITERS; ++it) {
     const int i = t + it * kWinThreads;
     const int gql = i / G, gj = i % G;
-    const int oslot = tile * kTileQ + gql;
+    const int oslot = tile * kWinTileQ + gql;
     int gq = -1;
     if (oslot < order_len) gq = order ? order[oslot] : oslot;
 #pragma unroll
@@ -602,7 +609,7 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
     for (int w = 0; w < warp; ++w) run += misc[w];
 #pragma unroll
     for (int k = 0; k < Cfg::SPT; ++k) { hist[t * Cfg::SPT + k] = run; run += v[k]; }
-    if (t == kWinThreads - 1) misc[8] = run;
+    if (t == kWinThreads - 1) misc[16] = run;
     __syncthreads();
   }
   // ---- place the sample ids at their sorted positions ---------------------------------------------
@@ -614,7 +621,7 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
       for (int i = 0; i < 4; ++i)
         if (rank[li][i] >= 0) {
           const int code = __float_as_int(rec[dql * Cfg::REC_STRIDE + l * 4 + i].x);
-          WIN_CHECK(hist[code & 0xffff] + rank[li][i] >= 0 && hist[code & 0xffff] + rank[li][i] < misc[8]);
+          WIN_CHECK(hist[code & 0xffff] + rank[li][i] >= 0 && hist[code & 0xffff] + rank[li][i] < misc[16]);
           sorted[hist[code & 0xffff] + rank[li][i]] = (unsigned short)(dql * LP + l * 4 + i);
         }
     }
@@ -635,7 +642,7 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
     float* gvalue_b = grad_value + img + oB / 4;
     const unsigned char* go_a = reinterpret_cast<const unsigned char*>(go_s) + oA;
     const unsigned char* go_b = reinterpret_cast<const unsigned char*>(go_s) + oB;
-    const int total = misc[8];
+    const int total = misc[16];
     const int chunk = (((total + SNG - 1) / SNG) + 3) & ~3;  // multiple of the batch size
     const int gi = warp * 8 + sg;
     const int i0 = min(total, gi * chunk), i1 = min(total, i0 + chunk);
@@ -688,7 +695,7 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
           }
           const int code = __float_as_int(r.x);
           const int row0 = code & 0xffff, row1 = code >> 16;
-          WIN_CHECK(sid < kTileQ * LP && row0 >= cur0 && row1 + 1 < kWinPool && row1 > row0);
+          WIN_CHECK(sid < kWinTileQ * LP && row0 >= cur0 && row1 + 1 < kWinPool && row1 > row0);
           if (row0 != cur0) {
             const bool adj = (row0 == cur0 + 1);
             if (cur0 >= 0) {
@@ -768,7 +775,7 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
   for (int l = 0; l < kL; ++l) all_win = all_win && wa.base[l] >= 0;
   if (!all_win) {
     const VT* value_j = value_img + j * C;
-    for (int ql = warp * GPW + g; ql < kTileQ; ql += NG) {
+    for (int ql = warp * GPW + g; ql < kWinTileQ; ql += NG) {
       float go[C];
 #pragma unroll
       for (int c = 0; c < C; c += 4) {

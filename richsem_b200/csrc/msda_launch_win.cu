@@ -13,7 +13,7 @@ int launch_fwd_win(cudaStream_t s, const Problem& pb, const VT* value, const flo
   auto kern = msda_fwd_d32_win_kernel<VT, kL, kM>;
   static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::FWD_SMEM);
   if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_fwd_d32_win_kernel)");
-  const int tiles = (pb.order_len + kTileQ - 1) / kTileQ;
+  const int tiles = (pb.order_len + kWinTileQ - 1) / kWinTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
   kern<<<grid, kWinThreads, Cfg::FWD_SMEM, s>>>(value, loc, attw, out, pb.order, pb.order_len, pb.lv,
                                                       pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
@@ -28,7 +28,7 @@ int launch_bwd_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* va
   auto kern = msda_bwd_d32_win_kernel<VT, kL, kM>;
   static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BWD_SMEM);
   if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_bwd_d32_win_kernel)");
-  const int tiles = (pb.order_len + kTileQ - 1) / kTileQ;
+  const int tiles = (pb.order_len + kWinTileQ - 1) / kWinTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
   kern<<<grid, kWinThreads, Cfg::BWD_SMEM, s>>>(go, value, loc, attw, gv, gl, ga, pb.order, pb.order_len, pb.lv,
                                                 pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
@@ -41,7 +41,7 @@ int launch_gradvalue(cudaStream_t s, const Problem& pb, const VT* go, const floa
   auto kern = msda_gradvalue_d32_kernel<VT, kL, kM>;
   static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_gradvalue_d32_kernel)");
-  const int tiles = (pb.order_len + kTileQ - 1) / kTileQ;
+  const int tiles = (pb.order_len + kWinTileQ - 1) / kWinTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
   kern<<<grid, kWinThreads, Cfg::SMEM_BYTES, s>>>(go, loc, attw, gv, pb.order, pb.order_len, pb.lv,
                                                   pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
