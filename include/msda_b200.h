@@ -69,6 +69,7 @@ extern "C" {
 #define MSDA_FLAG_COORDS_FMA 0x10u             /* pixel coordinate = fma(loc, size, -0.5): what nvcc -fmad=true makes of
                                                  cuh:285-286, i.e. the compiled reference; default is mul-then-sub  */
 #define MSDA_FLAG_NO_WINDOW 0x80u              /* backward: keep the L1-gather tiled kernel instead of the shared-memory window kernel */
+#define MSDA_FLAG_BWD_WS 0x1000u               /* backward: persistent warp-specialised window kernel (producer / consumer groups) */
 #define MSDA_FLAG_BWD_HALVES 0x800u            /* backward: gather kernel + cell-sorted grad_value kernel instead of the fused window kernel */
 #define MSDA_FLAG_NO_GRAD_VALUE 0x400u         /* backward: value needs no gradient; grad_value is not touched and may be NULL   */
 #define MSDA_FLAG_LDG256 0x200u                /* forward, fp32: 256-bit gathers, 4 lanes per (query, head) (opt-in, comparison)  */

@@ -28,6 +28,7 @@ FLAG_WINDOW_FWD = 0x100
 FLAG_LDG256 = 0x200
 FLAG_NO_GRAD_VALUE = 0x400
 FLAG_BWD_HALVES = 0x800
+FLAG_BWD_WS = 0x1000
 MAX_LEVELS = 16
 
 _vp, _i, _i64p = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)

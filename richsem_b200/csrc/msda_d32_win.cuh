@@ -65,7 +65,7 @@ constexpr int kWinPoolBwd = MSDA_WIN_POOL_BWD;
 __device__ unsigned long long g_win_timing[16];
 #define WIN_T(k, t0)                                                                          \
   do {                                                                                        \
-    if (threadIdx.x == 0) {                                                                   \
+    if ((threadIdx.x % kWinThreads) == 0) {                                                   \
       const long long now_ = clock64();                                                       \
       atomicAdd(&g_win_timing[k], (unsigned long long)(now_ - (t0)));                         \
       (t0) = now_;                                                                            \
@@ -139,7 +139,10 @@ struct WinCfg {
   static constexpr int OFF_HIST = OFF_GO + GO_BYTES;
   static constexpr int OFF_ROWOFF = OFF_HIST + HIST_BYTES;
   static constexpr int OFF_SORTED = OFF_ROWOFF + ROWOFF_BYTES;
-  static constexpr int BWD_SMEM = OFF_SORTED + SORTED_BYTES + 192;
+  static constexpr int INFLAG_BYTES = ((NLV * 4 * kWinTileQ + 127) / 128) * 128;
+  static constexpr int BWD_SMEM = OFF_SORTED + SORTED_BYTES + 192 + INFLAG_BYTES;
+  static constexpr int BWD_SET_BYTES = ((BWD_SMEM + 127) / 128) * 128;   // one buffer set of the warp-specialised kernel
+  static constexpr int BWD_WS_SMEM = 2 * BWD_SET_BYTES + 64;
   static_assert(kL <= 8, "per-level state is kept in 8-entry arrays");
   static_assert(kWinPool + 2 < 32768, "two pool rows are packed in one record word");
   static_assert(kWinTileQ * LP < 65536, "sample ids are stored as 16-bit");
@@ -173,14 +176,26 @@ __device__ __forceinline__ void win_allocate(const int* bb, WinAlloc<kL>& wa) {
   }
 }
 
+// How the threads that run a phase together synchronise: the whole block, or one 'kWinThreads'-wide group
+// of a warp-specialised block (named barrier kId).
+struct BlockSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+template <int kId>
+struct GroupSync {
+  __device__ __forceinline__ void operator()() const {
+    asm volatile("bar.sync %0, %1;" ::"n"(kId), "n"(kWinThreads) : "memory");
+  }
+};
+
 // Stages the windows of all allocated levels: warp w copies window lines w, w+8, ... of each level.
 // rowoff (backward only): per pool row, the element offset of the row inside the image's value block,
 // or -1 for rows outside the image.
 template <typename VT, int kL, bool kRowOff, int kWinPoolCheck>
 __device__ __forceinline__ void win_stage(const WinAlloc<kL>& wa, const MsdaLevels& lv, const VT* value_img,
-                                          const int m, const int M, unsigned char* pool, int* rowoff) {
+                                          const int m, const int M, unsigned char* pool, int* rowoff, const int t) {
   constexpr int ROWB = WinRow<VT>::ROWB, G = ROWB / 16, EPL = 16 / (int)sizeof(VT);  // elements per 16 B
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = t >> 5, lane = t & 31;
   const int rw0 = lane / G, jj = lane % G;
   const unsigned pool_s = smem_u32(pool);
 #pragma unroll
@@ -259,8 +274,8 @@ __device__ __forceinline__ void win_decode_level(const float* __restrict__ loc, 
 // allocation, staging (cp.async left in flight), records.  Thread t decodes level (t / 64) [+4] of
 // query t % 64, so the level is warp-uniform.  kBwd additionally fills rowoff and counts the windowed
 // samples per cell (hist; rank[][] = the sample's arrival order inside its cell).
-template <typename VT, int kL, int kWinPool, bool kBwd>
-__device__ __forceinline__ void win_front_end(const VT* __restrict__ value_img, const float* __restrict__ loc,
+template <typename VT, int kL, int kWinPool, bool kBwd, class Sync>
+__device__ __forceinline__ void win_front_end(const int t, const Sync sync, const VT* __restrict__ value_img, const float* __restrict__ loc,
                                               const float* __restrict__ attw, const int q, const size_t qm,
                                               const int qpf, const size_t qm_pf,
                                               const int m, const int M, const MsdaLevels& lv,
@@ -268,7 +283,7 @@ __device__ __forceinline__ void win_front_end(const VT* __restrict__ value_img, 
                                               WinAlloc<kL>& wa, WinPoint (&pts)[WinCfg<VT, kL, kWinPool>::NLV][4],
                                               int (&rank)[WinCfg<VT, kL, kWinPool>::NLV][4], long long& tph) {
   using Cfg = WinCfg<VT, kL, kWinPool>;
-  const int t = threadIdx.x, lane = t & 31;
+  const int lane = t & 31;
   const int ql = t & (kWinTileQ - 1), slot = t / kWinTileQ;
   if (t < 32) bb[t] = (t & 8) ? INT_MIN : INT_MAX;  // [0,8) hmin [8,16) hmax [16,24) wmin [24,32) wmax
   if (t >= 32 && t < 32 + 2 * Cfg::ROWB / 16)
@@ -277,7 +292,7 @@ __device__ __forceinline__ void win_front_end(const VT* __restrict__ value_img, 
 #pragma unroll
     for (int k = 0; k < Cfg::SPT; ++k) hist[t + k * kWinThreads] = 0;
   }
-  __syncthreads();
+  sync();
 #pragma unroll
   for (int li = 0; li < Cfg::NLV; ++li) {
     const int l = slot + 4 * li;  // warp-uniform
@@ -298,10 +313,10 @@ __device__ __forceinline__ void win_front_end(const VT* __restrict__ value_img, 
       }
     }
   }
-  __syncthreads();
-  WIN_T(kBwd ? 8 : 0, tph);  // decode + bounding boxes
+  sync();
+  if (!kBwd) WIN_T(0, tph);  // decode + bounding boxes
   win_allocate<kL, kWinPool>(bb, wa);
-  win_stage<VT, kL, kBwd, kWinPool>(wa, lv, value_img, m, M, pool, rowoff);
+  win_stage<VT, kL, kBwd, kWinPool>(wa, lv, value_img, m, M, pool, rowoff, t);
 #pragma unroll
   for (int li = 0; li < Cfg::NLV; ++li) {
     const int l = slot + 4 * li;
@@ -371,7 +386,7 @@ msda_fwd_d32_win_kernel(const VT* __restrict__ value, const float* __restrict__ 
     const size_t qm_pf = ((size_t)b * Lq + (qpf >= 0 ? qpf : 0)) * M + m;
     WinPoint pts[Cfg::NLV][4];
     int rank[Cfg::NLV][4];
-    win_front_end<VT, kL, kWinPool, false>(value_img, loc, attw, q, qm, qpf, qm_pf, m, M, lv, pool, rec, bb, nullptr, nullptr, wa, pts, rank, tphase);
+    win_front_end<VT, kL, kWinPool, false>(t, BlockSync{}, value_img, loc, attw, q, qm, qpf, qm_pf, m, M, lv, pool, rec, bb, nullptr, nullptr, wa, pts, rank, tphase);
   }
   WIN_T(1, tphase);  // allocation, staging issue, records
   cp_async_wait_all();
@@ -508,43 +523,63 @@ __device__ __forceinline__ void win_red_row(float* gvalue_j, const int off, cons
 #ifndef MSDA_WIN_BWD_MINBLOCKS
 #define MSDA_WIN_BWD_MINBLOCKS 2
 #endif
-template <typename VT, int kL, int kM>
-__global__ void __launch_bounds__(kWinThreads, MSDA_WIN_BWD_MINBLOCKS)
-msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
-                        const float* __restrict__ loc, const float* __restrict__ attw,
-                        float* __restrict__ grad_value, float* __restrict__ grad_loc,
-                        float* __restrict__ grad_attw, const int* __restrict__ order,
-                        const int order_len, const __grid_constant__ MsdaLevels lv, const int S,
-                        const int M_rt, const int Lq) {
-  constexpr int kWinPool = kWinPoolBwd;
+
+// Shared-memory working set of one backward tile (one "buffer set").
+template <class Cfg>
+struct WinBwdSmem {
+  unsigned char* pool;
+  float4* rec;
+  int* bb;
+  float* go_s;
+  int* hist;               // per-cell counts, then exclusive offsets
+  int* rowoff;
+  unsigned short* sorted;  // sample ids sorted by cell
+  int* misc;               // [0,16) warp totals [16] total [20,28) window base row per level (-1: direct)
+  float* lvf;              // [0,8) (float)W_l  [8,16) (float)H_l
+  unsigned char* inflag;   // per (level slot, query): bit i = point i passed the range test
+  __device__ __forceinline__ explicit WinBwdSmem(unsigned char* base)
+      : pool(base),
+        rec(reinterpret_cast<float4*>(base + Cfg::POOL_BYTES)),
+        bb(reinterpret_cast<int*>(base + Cfg::POOL_BYTES + Cfg::REC_BYTES)),
+        go_s(reinterpret_cast<float*>(base + Cfg::OFF_GO)),
+        hist(reinterpret_cast<int*>(base + Cfg::OFF_HIST)),
+        rowoff(reinterpret_cast<int*>(base + Cfg::OFF_ROWOFF)),
+        sorted(reinterpret_cast<unsigned short*>(base + Cfg::OFF_SORTED)),
+        misc(reinterpret_cast<int*>(base + Cfg::OFF_SORTED + Cfg::SORTED_BYTES)),
+        lvf(reinterpret_cast<float*>(base + Cfg::OFF_SORTED + Cfg::SORTED_BYTES) + 32),
+        inflag(base + Cfg::OFF_SORTED + Cfg::SORTED_BYTES + 192) {}
+};
+
+struct WinBwdArgs {
+  const void* grad_out;
+  const void* value;
+  const float* loc;
+  const float* attw;
+  float* grad_value;
+  float* grad_loc;
+  float* grad_attw;
+  const int* order;
+  int order_len, S, M, Lq;
+};
+
+// Producer half of a backward tile: decode, windows (staged with cp.async), records, counting sort,
+// grad_out rows.  `t` = thread index inside the kWinThreads-wide group that runs it, `sync` its barrier.
+// On return everything the consumer half needs is in the buffer set and visible to the group.
+template <typename VT, int kL, int kWinPool, class Sync>
+__device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, kWinPool>>& sm, const WinBwdArgs& ar,
+                                                const MsdaLevels& lv, const int tile, const int m, const int b,
+                                                const int t, const Sync sync) {
   using Cfg = WinCfg<VT, kL, kWinPool>;
   using RT = RowTraits<VT>;
-  using WR = WinRow<VT>;
-  constexpr int LP = Cfg::LP, G = RT::G, C = RT::C, GPW = 32 / G, ROWB = Cfg::ROWB;
-  constexpr int NG = (kWinThreads / 32) * GPW;  // lane groups per block
-  static_assert(kWinTileQ * 4 == kWinThreads, "decode maps 4 threads to a query");
+  constexpr int LP = Cfg::LP, G = RT::G, C = RT::C;
+  const int M = ar.M, Lq = ar.Lq;
+  const int warp = t >> 5, lane = t & 31;
+  const VT* grad_out = static_cast<const VT*>(ar.grad_out);
+  const VT* value_img = static_cast<const VT*>(ar.value) + (size_t)b * ar.S * M * 32;
+  const int* order = ar.order;
+  const int order_len = ar.order_len;
+  long long tphase = 0;
 
-  extern __shared__ __align__(128) unsigned char smraw[];
-  unsigned char* pool = smraw;
-  float4* rec = reinterpret_cast<float4*>(smraw + Cfg::POOL_BYTES);
-  int* bb = reinterpret_cast<int*>(smraw + Cfg::POOL_BYTES + Cfg::REC_BYTES);
-  float* go_s = reinterpret_cast<float*>(smraw + Cfg::OFF_GO);
-  int* hist = reinterpret_cast<int*>(smraw + Cfg::OFF_HIST);       // counts, then exclusive offsets
-  int* rowoff = reinterpret_cast<int*>(smraw + Cfg::OFF_ROWOFF);
-  unsigned short* sorted = reinterpret_cast<unsigned short*>(smraw + Cfg::OFF_SORTED);
-  int* misc = reinterpret_cast<int*>(smraw + Cfg::OFF_SORTED + Cfg::SORTED_BYTES);  // [0,16) warp totals [16] total
-  float* lvf = reinterpret_cast<float*>(misc + 32);  // [0,8) (float)W_l  [8,16) (float)H_l
-
-  const int M = kM ? kM : M_rt;
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int m = blockIdx.x % M, tile = blockIdx.x / M, b = blockIdx.y;
-  const int M32 = M * 32;
-  const size_t img = (size_t)b * S * M32;
-  const VT* value_img = value + img;
-
-  // ---- front end -------------------------------------------------------------------------------
-  long long tphase = clock64();
-  (void)tphase;
   const int dql = t & (kWinTileQ - 1), dslot = t / kWinTileQ;
   int dq = -1;
   {
@@ -578,39 +613,49 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
   WinAlloc<kL> wa;
   WinPoint pts[Cfg::NLV][4];
   int rank[Cfg::NLV][4];
-  win_front_end<VT, kL, kWinPool, true>(value_img, loc, attw, dq, dqm, qpf, qm_pf, m, M, lv, pool, rec, bb, rowoff, hist, wa, pts, rank, tphase);
+  win_front_end<VT, kL, kWinPool, true>(t, sync, value_img, ar.loc, ar.attw, dq, dqm, qpf, qm_pf, m, M, lv, sm.pool, sm.rec,
+                                        sm.bb, sm.rowoff, sm.hist, wa, pts, rank, tphase);
 #pragma unroll
   for (int it = 0; it < GO_ITERS; ++it) {
     const int i = t + it * kWinThreads;
 #pragma unroll
     for (int c = 0; c < C; c += 4)
-      *reinterpret_cast<float4*>(go_s + (i / G) * 32 + (i % G) * C + c) =
+      *reinterpret_cast<float4*>(sm.go_s + (i / G) * 32 + (i % G) * C + c) =
           make_float4(gvreg[it][c], gvreg[it][c + 1], gvreg[it][c + 2], gvreg[it][c + 3]);
   }
-  if (t < 2) rowoff[kWinPool + t] = -1;
-  if (t >= 32 && t < 32 + kL) { lvf[t - 32] = (float)lv.W[t - 32]; lvf[8 + t - 32] = (float)lv.H[t - 32]; }
-  __syncthreads();  // hist complete, records visible
-  WIN_T(9, tphase);  // allocation, staging issue, records, histogram
+#pragma unroll
+  for (int li = 0; li < Cfg::NLV; ++li)
+    sm.inflag[(li * 4 + dslot) * kWinTileQ + dql] =
+        (unsigned char)((pts[li][0].in ? 1 : 0) | (pts[li][1].in ? 2 : 0) | (pts[li][2].in ? 4 : 0) | (pts[li][3].in ? 8 : 0));
+  if (t < 2) sm.rowoff[kWinPool + t] = -1;
+  if (t >= 32 && t < 32 + kL) {
+    sm.lvf[t - 32] = (float)lv.W[t - 32];
+    sm.lvf[8 + t - 32] = (float)lv.H[t - 32];
+#pragma unroll
+    for (int l = 0; l < kL; ++l)
+      if (l == t - 32) sm.misc[20 + l] = wa.base[l];
+  }
+  sync();  // hist complete, records visible
 
   // ---- exclusive scan of the per-cell counts, in place -----------------------------------------
   {
     int v[Cfg::SPT], sum = 0;
 #pragma unroll
-    for (int k = 0; k < Cfg::SPT; ++k) { v[k] = hist[t * Cfg::SPT + k]; sum += v[k]; }
+    for (int k = 0; k < Cfg::SPT; ++k) { v[k] = sm.hist[t * Cfg::SPT + k]; sum += v[k]; }
     int inc = sum;
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1) {
       const int n = __shfl_up_sync(0xffffffffu, inc, s);
       if (lane >= s) inc += n;
     }
-    if (lane == 31) misc[warp] = inc;
-    __syncthreads();
+    if (lane == 31) sm.misc[warp] = inc;
+    sync();
     int run = inc - sum;
-    for (int w = 0; w < warp; ++w) run += misc[w];
+    for (int w = 0; w < warp; ++w) run += sm.misc[w];
 #pragma unroll
-    for (int k = 0; k < Cfg::SPT; ++k) { hist[t * Cfg::SPT + k] = run; run += v[k]; }
-    if (t == kWinThreads - 1) misc[16] = run;
-    __syncthreads();
+    for (int k = 0; k < Cfg::SPT; ++k) { sm.hist[t * Cfg::SPT + k] = run; run += v[k]; }
+    if (t == kWinThreads - 1) sm.misc[16] = run;
+    sync();
   }
   // ---- place the sample ids at their sorted positions ---------------------------------------------
 #pragma unroll
@@ -620,16 +665,41 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         if (rank[li][i] >= 0) {
-          const int code = __float_as_int(rec[dql * Cfg::REC_STRIDE + l * 4 + i].x);
-          WIN_CHECK(hist[code & 0xffff] + rank[li][i] >= 0 && hist[code & 0xffff] + rank[li][i] < misc[16]);
-          sorted[hist[code & 0xffff] + rank[li][i]] = (unsigned short)(dql * LP + l * 4 + i);
+          const int code = __float_as_int(sm.rec[dql * Cfg::REC_STRIDE + l * 4 + i].x);
+          WIN_CHECK(sm.hist[code & 0xffff] + rank[li][i] >= 0 && sm.hist[code & 0xffff] + rank[li][i] < sm.misc[16]);
+          sm.sorted[sm.hist[code & 0xffff] + rank[li][i]] = (unsigned short)(dql * LP + l * 4 + i);
         }
     }
   }
-  WIN_T(10, tphase);  // scan + placement
   cp_async_wait_all();
-  __syncthreads();  // windows, sorted list, grad_out rows are in shared memory
-  WIN_T(11, tphase);  // wait for the windows
+  sync();  // windows, sorted list, grad_out rows are in shared memory
+}
+
+// Consumer half: sorted pass, direct pass, write-out (see the file header).
+template <typename VT, int kL, int kWinPool, class Sync>
+__device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, kWinPool>>& sm, const WinBwdArgs& ar,
+                                                const MsdaLevels& lv, const int tile, const int m, const int b,
+                                                const int t, const Sync sync) {
+  using Cfg = WinCfg<VT, kL, kWinPool>;
+  using RT = RowTraits<VT>;
+  constexpr int LP = Cfg::LP, G = RT::G, C = RT::C, GPW = 32 / G, ROWB = Cfg::ROWB;
+  constexpr int NG = (kWinThreads / 32) * GPW;  // lane groups per block
+  const int M = ar.M, Lq = ar.Lq, S = ar.S;
+  const int M32 = M * 32;
+  const int warp = t >> 5, lane = t & 31;
+  const size_t img = (size_t)b * S * M32;
+  const VT* value_img = static_cast<const VT*>(ar.value) + img;
+  float* grad_value = ar.grad_value;
+  unsigned char* pool = sm.pool;
+  float4* rec = sm.rec;
+  float* go_s = sm.go_s;
+  int* rowoff = sm.rowoff;
+  unsigned short* sorted = sm.sorted;
+  int* misc = sm.misc;
+  float* lvf = sm.lvf;
+  int lbase[kL];
+#pragma unroll
+  for (int l = 0; l < kL; ++l) lbase[l] = misc[20 + l];
 
   // ---- sorted pass: one 4-lane group (8 channels per lane) per contiguous chunk of the cell-sorted samples ----
   {
@@ -765,14 +835,10 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
   const int g = lane / G, j = lane % G;
   float* gvalue_j = grad_value + img + j * C;
 
-#ifdef MSDA_WIN_TIMING
-  __syncthreads();
-  WIN_T(12, tphase);  // sorted pass
-#endif
   // ---- direct pass: levels that did not get a window, query-major from global memory -------------------
   bool all_win = true;
 #pragma unroll
-  for (int l = 0; l < kL; ++l) all_win = all_win && wa.base[l] >= 0;
+  for (int l = 0; l < kL; ++l) all_win = all_win && lbase[l] >= 0;
   if (!all_win) {
     const VT* value_j = value_img + j * C;
     for (int ql = warp * GPW + g; ql < kWinTileQ; ql += NG) {
@@ -784,7 +850,7 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
       }
 #pragma unroll
       for (int l = 0; l < kL; ++l) {
-        if (wa.base[l] >= 0) continue;  // block-uniform
+        if (lbase[l] >= 0) continue;  // block-uniform
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4* slot = rec + ql * Cfg::REC_STRIDE + l * 4 + i;
@@ -827,29 +893,126 @@ msda_bwd_d32_win_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
       }
     }
   }
-  __syncthreads();  // every sample's gradients are parked in its record slot
-  WIN_T(13, tphase);  // direct pass
-#ifdef MSDA_WIN_TIMING
-  if (threadIdx.x == 0) atomicAdd(&g_win_timing[15], 1ull);
-#endif
+  sync();  // every sample's gradients are parked in its record slot
 
-  // ---- write-out: same thread <-> (level, query) mapping as the decode ------------------------------------
+  // ---- write-out: thread <-> (level slot, query) as in the decode ------------------------------------
+  const int dql = t & (kWinTileQ - 1), dslot = t / kWinTileQ;
+  int dq = -1;
+  {
+    const int oslot = tile * kWinTileQ + dql;
+    if (oslot < ar.order_len) dq = ar.order ? ar.order[oslot] : oslot;
+  }
   if (dq >= 0) {
+    const size_t dqm = ((size_t)b * Lq + dq) * M + m;
 #pragma unroll
     for (int li = 0; li < Cfg::NLV; ++li) {
       const int l = dslot + 4 * li;
       if (l < kL) {
+        const int fl = sm.inflag[(li * 4 + dslot) * kWinTileQ + dql];
         float4 r[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           r[i] = rec[dql * Cfg::REC_STRIDE + l * 4 + i];
-          if (!pts[li][i].in) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // skipped sample: slot still holds its record
+          if (!(fl & (1 << i))) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // skipped sample: slot still holds its record
         }
-        float* gl = grad_loc + (dqm * LP + l * 4) * 2;
+        float* gl = ar.grad_loc + (dqm * LP + l * 4) * 2;
         st_stream_f4(gl, make_float4(r[0].x, r[0].y, r[1].x, r[1].y));
         st_stream_f4(gl + 4, make_float4(r[2].x, r[2].y, r[3].x, r[3].y));
-        st_stream_f4(grad_attw + dqm * LP + l * 4, make_float4(r[0].z, r[1].z, r[2].z, r[3].z));
+        st_stream_f4(ar.grad_attw + dqm * LP + l * 4, make_float4(r[0].z, r[1].z, r[2].z, r[3].z));
       }
+    }
+  }
+}
+
+// One block = one tile x one head: produce, then consume.
+template <typename VT, int kL, int kM>
+__global__ void __launch_bounds__(kWinThreads, MSDA_WIN_BWD_MINBLOCKS)
+msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels lv) {
+  constexpr int kWinPool = kWinPoolBwd;
+  using Cfg = WinCfg<VT, kL, kWinPool>;
+  static_assert(kWinTileQ * 4 == kWinThreads, "decode maps 4 threads to a query");
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const WinBwdSmem<Cfg> sm(smraw);
+  WinBwdArgs a = ar;
+  if (kM) a.M = kM;
+  const int m = blockIdx.x % a.M, tile = blockIdx.x / a.M, b = blockIdx.y;
+  win_bwd_produce<VT, kL, kWinPool>(sm, a, lv, tile, m, b, (int)threadIdx.x, BlockSync{});
+  win_bwd_consume<VT, kL, kWinPool>(sm, a, lv, tile, m, b, (int)threadIdx.x, BlockSync{});
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, persistent and warp-specialised: one block per SM with two kWinThreads-wide groups.  The
+// producer group runs the front end of tile i+1 into one buffer set while the consumer group runs the
+// sorted pass of tile i out of the other, so the front end's load latencies and barriers overlap the
+// sorted pass's arithmetic instead of alternating with it.  Hand-off through two pairs of mbarriers
+// (full / empty per buffer set), barriers inside a group are named barriers (bar.sync id, 256).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, const int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, const unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  unsigned done = 0;
+#ifdef MSDA_WIN_CHECKS
+  long long spins = 0;
+#endif
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+#ifdef MSDA_WIN_CHECKS
+    if (++spins > (1ll << 26)) asm volatile("trap;");  // a lost hand-off must not hang the GPU
+#endif
+  }
+}
+
+template <typename VT, int kL, int kM>
+__global__ void __launch_bounds__(2 * kWinThreads, 1)
+msda_bwd_d32_ws_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels lv, const int tiles, const int batch) {
+  constexpr int kWinPool = kWinPoolBwd;
+  using Cfg = WinCfg<VT, kL, kWinPool>;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smraw + 2 * Cfg::BWD_SET_BYTES);  // full[2], empty[2]
+  WinBwdArgs a = ar;
+  if (kM) a.M = kM;
+  const int role = threadIdx.x / kWinThreads, t = threadIdx.x % kWinThreads;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int total = tiles * a.M * batch;
+  int it = 0;
+  for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+    const int set = it & 1;
+    const unsigned use = (unsigned)(it >> 1);  // how many times this buffer set has been used before
+    const WinBwdSmem<Cfg> sm(smraw + set * Cfg::BWD_SET_BYTES);
+    const int m = w % a.M, tb = w / a.M;
+    const int tile = tb % tiles, b = tb / tiles;
+    long long tph = clock64();
+    (void)tph;
+    if (role == 0) {
+      if (use > 0) mbar_wait(bars + 2 + set, (use - 1) & 1);  // the consumer released the set
+      if (t == 0) WIN_T(11, tph);  // producer waiting for a free buffer set
+      win_bwd_produce<VT, kL, kWinPool>(sm, a, lv, tile, m, b, t, GroupSync<1>{});
+      if (t == 0) WIN_T(8, tph);   // produce
+      if (t == 0) mbar_arrive(bars + set);
+    } else {
+      mbar_wait(bars + set, use & 1);
+      if (t == 0) WIN_T(9, tph);   // consumer waiting for a full buffer set
+      win_bwd_consume<VT, kL, kWinPool>(sm, a, lv, tile, m, b, t, GroupSync<2>{});
+      GroupSync<2>{}();  // every consumer thread is done with the set
+      if (t == 0) WIN_T(10, tph);  // consume
+#ifdef MSDA_WIN_TIMING
+      if (t == 0) atomicAdd(&g_win_timing[15], 1ull);
+#endif
+      if (t == 0) mbar_arrive(bars + 2 + set);
     }
   }
 }

@@ -21,6 +21,17 @@ int launch_fwd_win(cudaStream_t s, const Problem& pb, const VT* value, const flo
 }
 
 
+template <typename VT>
+WinBwdArgs make_bwd_args(const Problem& pb, const VT* go, const VT* value, const float* loc, const float* attw,
+                         float* gv, float* gl, float* ga) {
+  WinBwdArgs a;
+  a.grad_out = go; a.value = value; a.loc = loc; a.attw = attw;
+  a.grad_value = gv; a.grad_loc = gl; a.grad_attw = ga;
+  a.order = pb.order; a.order_len = pb.order_len;
+  a.S = pb.d.spatial_size; a.M = pb.d.num_heads; a.Lq = pb.d.num_query;
+  return a;
+}
+
 template <typename VT, int kL, int kM>
 int launch_bwd_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
                    const float* attw, float* gv, float* gl, float* ga) {
@@ -30,9 +41,28 @@ int launch_bwd_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* va
   if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_bwd_d32_win_kernel)");
   const int tiles = (pb.order_len + kWinTileQ - 1) / kWinTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
-  kern<<<grid, kWinThreads, Cfg::BWD_SMEM, s>>>(go, value, loc, attw, gv, gl, ga, pb.order, pb.order_len, pb.lv,
-                                                pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
+  kern<<<grid, kWinThreads, Cfg::BWD_SMEM, s>>>(make_bwd_args(pb, go, value, loc, attw, gv, gl, ga), pb.lv);
   return after_launch("msda_bwd_d32_win_kernel");
+}
+
+// persistent, warp-specialised variant: one 2 x kWinThreads block per SM
+template <typename VT, int kL, int kM>
+int launch_bwd_ws(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
+                  const float* attw, float* gv, float* gl, float* ga) {
+  using Cfg = WinCfg<VT, kL, kWinPoolBwd>;
+  auto kern = msda_bwd_d32_ws_kernel<VT, kL, kM>;
+  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BWD_WS_SMEM);
+  if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_bwd_d32_ws_kernel)");
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return check_cuda(e, "cudaDeviceGetAttribute(MultiProcessorCount)");
+  const int tiles = (pb.order_len + kWinTileQ - 1) / kWinTileQ;
+  const long long total = (long long)tiles * pb.d.num_heads * pb.d.batch;
+  const int grid = (int)(total < sms ? total : sms);
+  kern<<<grid, 2 * kWinThreads, Cfg::BWD_WS_SMEM, s>>>(make_bwd_args(pb, go, value, loc, attw, gv, gl, ga), pb.lv, tiles,
+                                                      pb.d.batch);
+  return after_launch("msda_bwd_d32_ws_kernel");
 }
 
 template <typename VT, int kL, int kM>
@@ -73,6 +103,12 @@ int fwd_d32_win(cudaStream_t s, const Problem& pb, const VT* value, const float*
 template <typename VT>
 int bwd_d32_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
                 const float* attw, float* gv, float* gl, float* ga) {
+  if (pb.flags & MSDA_FLAG_BWD_WS) {
+    if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_bwd_ws<VT, 4, 8>(s, pb, go, value, loc, attw, gv, gl, ga);
+#define CALL(L) launch_bwd_ws<VT, L, 0>(s, pb, go, value, loc, attw, gv, gl, ga)
+    MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+  }
   if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_bwd_win<VT, 4, 8>(s, pb, go, value, loc, attw, gv, gl, ga);
 #define CALL(L) launch_bwd_win<VT, L, 0>(s, pb, go, value, loc, attw, gv, gl, ga)
   MSDA_SWITCH_L(pb.d.num_levels, CALL)

@@ -19,7 +19,7 @@ nb = max(t[7], 1)
 print("fwd blocks", nb // n, "cycles/block: decode+bbox %.0f | alloc+stage+records %.0f | window wait %.0f | gather %.0f" % tuple(x / nb for x in t[0:4]))
 print("  fwd gather: blocks with a direct level %d of %d, their gather %.0f cycles, fully windowed blocks %.0f" % (t[5] // n, nb // n, t[4] / max(t[5], 1), (t[3] - t[4]) / max(nb - t[5], 1)))
 for _ in range(n):
-    ext.ms_deform_attn_backward(*args, i["grad_out"], 64)
+    ext.ms_deform_attn_backward(*args, i["grad_out"], 64, _flags=_capi.FLAG_BWD_WS)
 lib.msda_debug_win_timing(buf); t = list(buf)
 nb = max(t[15], 1)
-print("bwd blocks", nb // n, "cycles/block: decode+bbox %.0f | alloc+stage+records+hist %.0f | scan+place %.0f | window wait %.0f | sorted pass %.0f | direct pass %.0f" % tuple(x / nb for x in t[8:14]))
+print("bwd warp-specialised, tiles", nb // n, "cycles/tile: produce %.0f | consumer waits %.0f | consume %.0f | producer waits %.0f" % tuple(x / nb for x in t[8:12]))

@@ -40,7 +40,7 @@ def test_extension_is_loaded_from_the_tree():
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-@pytest.mark.parametrize("path", ["auto", "halves", "window", "tiled", "tiled256", "generic"])
+@pytest.mark.parametrize("path", ["auto", "halves", "window", "ws", "tiled", "tiled256", "generic"])
 def test_golden_forward_backward(case, path):
     """auto = what the library picks (warp-per-query "split" kernels at these sizes for D=32);
     window = the shared-memory window kernels used for large problems; tiled = their L1-gather
@@ -52,6 +52,7 @@ def test_golden_forward_backward(case, path):
     v, shp, st, loc, w, go = _to_dev(g)
     flags = {"auto": 0, "halves": _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_HALVES,
              "window": _capi.FLAG_NO_SPLIT | _capi.FLAG_WINDOW_FWD,
+             "ws": _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_WS,
              "tiled": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW,
              "tiled256": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW | _capi.FLAG_LDG256,
              "generic": _capi.FLAG_FORCE_GENERIC}[path]
@@ -137,7 +138,8 @@ def test_gradcheck_like_reference(channels):
     assert gradcheck(MSDeformAttnFunction.apply, (value, shapes, starts, loc, w, 2))
 
 
-@pytest.mark.parametrize("kind,n,lq,bflags", [("E", 1, None, 0), ("E", 1, None, "halves"), ("E", 1, None, "tiled"),
+@pytest.mark.parametrize("kind,n,lq,bflags", [("E", 1, None, 0), ("E", 2, None, "ws"), ("E", 1, None, "halves"), ("E", 1, None, "tiled"),
+                                              ("U", 2, 3000, "ws"),
                                               ("U", 2, 3000, 0), ("U", 2, 3000, "halves"), ("U", 2, 3000, "window"),
                                               ("Dn", 2, 1100, 0), ("Dn", 2, 1100, "window")])
 def test_dino_shape_against_c_oracle(kind, n, lq, bflags, c_oracle):
@@ -147,7 +149,7 @@ def test_dino_shape_against_c_oracle(kind, n, lq, bflags, c_oracle):
     "tiled" = per-corner reductions, "window" = the fused window kernel forced on small / non-local inputs."""
     from richsem_b200 import _capi, synthetic as syn
 
-    bflags = {0: 0, "window": _capi.FLAG_NO_SPLIT, "halves": _capi.FLAG_BWD_HALVES | _capi.FLAG_NO_SPLIT,
+    bflags = {0: 0, "window": _capi.FLAG_NO_SPLIT, "ws": _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_WS, "halves": _capi.FLAG_BWD_HALVES | _capi.FLAG_NO_SPLIT,
               "tiled": _capi.FLAG_NO_WINDOW}[bflags]
     shapes = syn.level_shapes(800, 1333)
     i = syn.make_inputs(kind, n, shapes, "cuda:0", seed=21, lq=lq)
@@ -248,7 +250,7 @@ def test_window_backward_matches_tiled_backward_bf16_and_five_levels():
         i = syn.make_inputs("E", 2, shapes, "cuda:0", seed=4, dtype=dtype)
         args = (i["value"], i["shapes"], i["starts"], i["loc"], i["attw"], i["grad_out"], 64)
         y = b(*args, _flags=_capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW)
-        for fl in (_capi.FLAG_NO_SPLIT, _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_HALVES):
+        for fl in (_capi.FLAG_NO_SPLIT, _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_HALVES, _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_WS):
             x = b(*args, _flags=fl)
             assert rel_err(x[0], y[0]) < 1e-5
             assert rel_err(x[1], y[1]) < 1e-5 and rel_err(x[2], y[2]) < 1e-5
