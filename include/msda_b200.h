@@ -63,7 +63,8 @@ extern "C" {
 #define MSDA_ERR_WORKSPACE 4        /* deterministic mode: workspace missing/small */
 
 /* msda_opts.flags */
-#define MSDA_FLAG_DETERMINISTIC 0x1u          /* grad_value via sort-by-corner segmented sum, bitwise reproducible */
+#define MSDA_FLAG_DETERMINISTIC 0x1u          /* bitwise reproducible grad_value (fixed-point accumulation of canonically
+                                                 ordered partial sums, or sort-by-corner segmented sums); needs workspace */
 #define MSDA_FLAG_GRAD_VALUE_PREZEROED 0x2u   /* caller already zeroed grad_value (or wants accumulation)           */
 #define MSDA_FLAG_FORCE_GENERIC 0x4u          /* bypass the D=32 fast kernels (testing)                             */
 #define MSDA_FLAG_COORDS_FMA 0x10u             /* pixel coordinate = fma(loc, size, -0.5): what nvcc -fmad=true makes of

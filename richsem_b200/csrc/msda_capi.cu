@@ -167,6 +167,10 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
                       aligned(value, 16) && aligned(gv, 16) && aligned(loc, 16) && aligned(attw, 16) &&
                       aligned(grad_out, 16) && aligned(gl, 8);
     if (fast && no_gv) return msda::bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
+    // deterministic, large problem: the window kernel with canonical in-block order and fixed-point accumulation
+    if (fast && det && !msda::use_split(pb) && !(pb.flags & MSDA_FLAG_NO_WINDOW))
+      return msda::bwd_d32_win_det<TV>(s, pb, grad_out, value, loc, attw, gv, gl, ga, opts ? opts->workspace : nullptr,
+                                       opts ? opts->workspace_bytes : 0);
     if (fast) {
       // large problems: the fused window kernel (0.414 ms per bs=2 encoder layer).  MSDA_FLAG_BWD_HALVES runs
       // the two halves of the backward as two kernels instead — gather + dot products for grad_sampling_loc /

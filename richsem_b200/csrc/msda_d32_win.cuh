@@ -560,12 +560,48 @@ struct WinBwdArgs {
   float* grad_attw;
   const int* order;
   int order_len, S, M, Lq;
+  // deterministic mode only: fixed-point accumulators (one per grad_value element) and the bit patterns of
+  // max|grad_out|, max|attn_weight| that fix their scale
+  long long* gv64;
+  const unsigned* maxbits;
 };
+
+// Deterministic mode: scale (a power of two) that maps any sum of up to Lq*L*P products weight * grad_out,
+// |weight| <= max|attn_weight|, into 62 bits.  Integer addition is associative, so the order in which blocks
+// add their (canonically computed) partial sums no longer matters.
+__device__ __forceinline__ int win_det_shift(const unsigned* maxbits, const int Lq, const int LP) {
+  const int e_go = (int)((maxbits[0] >> 23) & 0xff) - 126;  // max|grad_out| < 2^e_go
+  const int e_a = (int)((maxbits[1] >> 23) & 0xff) - 126;
+  const int e_n = 32 - __clz(max(Lq * LP, 1));                // Lq*L*P < 2^e_n
+  return max(-120, min(120, 62 - (e_go + e_a + e_n)));        // the scale 2^shift is an fp32 normal
+}
+__device__ __forceinline__ float win_det_scale(const unsigned* maxbits, const int Lq, const int LP) {
+  return __uint_as_float((unsigned)(127 + win_det_shift(maxbits, Lq, LP)) << 23);
+}
+// v * 2^shift is exact in fp32 (no overflow by construction), so one FMUL and one F2I do the conversion
+__device__ __forceinline__ void win_det_add(long long* p, const float v, const float scale) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__float2ll_rn(v * scale));
+}
+// 4x4 transpose over the 4 lanes of a quad (q = lane & 3): afterwards a[L] is what lane L of the quad held in
+// a[q].  Lets the four lanes of one 64-bit reduction instruction hit four CONSECUTIVE accumulators (one 32-byte
+// sector) instead of four sectors — L2 retires atomics per sector.
+__device__ __forceinline__ void quad_transpose4(float (&a)[4], const int q, const unsigned mask) {
+  {
+    const bool hi = q & 1;
+    const float r0 = __shfl_xor_sync(mask, hi ? a[0] : a[1], 1), r1 = __shfl_xor_sync(mask, hi ? a[2] : a[3], 1);
+    if (hi) { a[0] = r0; a[2] = r1; } else { a[1] = r0; a[3] = r1; }
+  }
+  {
+    const bool hi = q & 2;
+    const float r0 = __shfl_xor_sync(mask, hi ? a[0] : a[2], 2), r1 = __shfl_xor_sync(mask, hi ? a[1] : a[3], 2);
+    if (hi) { a[0] = r0; a[1] = r1; } else { a[2] = r0; a[3] = r1; }
+  }
+}
 
 // Producer half of a backward tile: decode, windows (staged with cp.async), records, counting sort,
 // grad_out rows.  `t` = thread index inside the kWinThreads-wide group that runs it, `sync` its barrier.
 // On return everything the consumer half needs is in the buffer set and visible to the group.
-template <typename VT, int kL, int kWinPool, class Sync>
+template <typename VT, int kL, int kWinPool, bool kDet, class Sync>
 __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, kWinPool>>& sm, const WinBwdArgs& ar,
                                                 const MsdaLevels& lv, const int tile, const int m, const int b,
                                                 const int t, const Sync sync) {
@@ -671,12 +707,27 @@ __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, 
         }
     }
   }
+  if (kDet) {
+    // canonical order inside every cell: the ranks above are arrival orders of shared-memory atomics, so
+    // each cell's run of sample ids is sorted before anything is summed (runs are short: ~3 ids)
+    sync();
+    const int total = sm.misc[16];
+    for (int c = t; c < kWinPool; c += kWinThreads) {
+      const int beg = sm.hist[c], end = (c + 1 < Cfg::HIST_N) ? sm.hist[c + 1] : total;
+      for (int i = beg + 1; i < end; ++i) {
+        const unsigned short key = sm.sorted[i];
+        int k = i - 1;
+        while (k >= beg && sm.sorted[k] > key) { sm.sorted[k + 1] = sm.sorted[k]; --k; }
+        sm.sorted[k + 1] = key;
+      }
+    }
+  }
   cp_async_wait_all();
   sync();  // windows, sorted list, grad_out rows are in shared memory
 }
 
 // Consumer half: sorted pass, direct pass, write-out (see the file header).
-template <typename VT, int kL, int kWinPool, class Sync>
+template <typename VT, int kL, int kWinPool, bool kDet, class Sync>
 __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, kWinPool>>& sm, const WinBwdArgs& ar,
                                                 const MsdaLevels& lv, const int tile, const int m, const int b,
                                                 const int t, const Sync sync) {
@@ -700,6 +751,8 @@ __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, 
   int lbase[kL];
 #pragma unroll
   for (int l = 0; l < kL; ++l) lbase[l] = misc[20 + l];
+  const float dscale = kDet ? win_det_scale(ar.maxbits, Lq, LP) : 0.f;
+  long long* gv64 = kDet ? ar.gv64 + img : nullptr;
 
   // ---- sorted pass: one 4-lane group (8 channels per lane) per contiguous chunk of the cell-sorted samples ----
   {
@@ -729,8 +782,21 @@ __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, 
       const int off = rowoff[row];
       WIN_CHECK(off < 0 || (off % 32 == 0 && off / 32 < S * M));
       if (off >= 0) {
-        red_add_f4(gvalue_a + off, acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-        red_add_f4(gvalue_b + off, acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+        if (kDet) {
+          // lane sj holds chunks cA, cB (4 channels each); after the quad transposes it holds element sj of
+          // every lane's chunk, so the 4 lanes of one reduction instruction cover one chunk = one 32-byte sector
+          float ta[4] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y}, tb[4] = {acc[2].x, acc[2].y, acc[3].x, acc[3].y};
+          quad_transpose4(ta, sj, gmask);
+          quad_transpose4(tb, sj, gmask);
+#pragma unroll
+          for (int L = 0; L < 4; ++L) {  // ta[L] / tb[L]: element sj of lane L's chunk a / b
+            win_det_add(gv64 + off + SL::chunk_a(sg, L) * 4 + sj, ta[L], dscale);
+            win_det_add(gv64 + off + SL::chunk_b(sg, L) * 4 + sj, tb[L], dscale);
+          }
+        } else {
+          red_add_f4(gvalue_a + off, acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+          red_add_f4(gvalue_b + off, acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+        }
       }
     };
     auto load_row = [&](const int row, float2 (&v)[SP]) {
@@ -869,9 +935,21 @@ __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, 
               float v[C];
               RT::load(value_j + o, v);
               const float tt = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
+              if (kDet) {
+                const unsigned qmask = 0xfu << (lane & ~3);
 #pragma unroll
-              for (int c = 0; c < C; c += 4)
-                red_add_f4(gvalue_j + o + c, tt * go[c], tt * go[c + 1], tt * go[c + 2], tt * go[c + 3]);
+                for (int c = 0; c < C; c += 4) {
+                  float tq[4] = {tt * go[c], tt * go[c + 1], tt * go[c + 2], tt * go[c + 3]};
+                  quad_transpose4(tq, j & 3, qmask);
+#pragma unroll
+                  for (int L = 0; L < 4; ++L)  // lane L of the quad held channels (j & ~3 | L) * C + c .. + 3
+                    win_det_add(gv64 + o + ((j & ~3) + L) * C + c + (j & 3), tq[L], dscale);
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < C; c += 4)
+                  red_add_f4(gvalue_j + o + c, tt * go[c], tt * go[c + 1], tt * go[c + 2], tt * go[c + 3]);
+              }
               float sdot = 0.f;
 #pragma unroll
               for (int c = 0; c < C; ++c) sdot = fmaf(go[c], v[c], sdot);
@@ -924,8 +1002,9 @@ __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, 
   }
 }
 
-// One block = one tile x one head: produce, then consume.
-template <typename VT, int kL, int kM>
+// One block = one tile x one head: produce, then consume.  kDet: deterministic grad_value (canonical order
+// inside the block, order-independent fixed-point accumulation across blocks; see msda_capi.cu).
+template <typename VT, int kL, int kM, bool kDet>
 __global__ void __launch_bounds__(kWinThreads, MSDA_WIN_BWD_MINBLOCKS)
 msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels lv) {
   constexpr int kWinPool = kWinPoolBwd;
@@ -936,8 +1015,27 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
   WinBwdArgs a = ar;
   if (kM) a.M = kM;
   const int m = blockIdx.x % a.M, tile = blockIdx.x / a.M, b = blockIdx.y;
-  win_bwd_produce<VT, kL, kWinPool>(sm, a, lv, tile, m, b, (int)threadIdx.x, BlockSync{});
-  win_bwd_consume<VT, kL, kWinPool>(sm, a, lv, tile, m, b, (int)threadIdx.x, BlockSync{});
+  win_bwd_produce<VT, kL, kWinPool, kDet>(sm, a, lv, tile, m, b, (int)threadIdx.x, BlockSync{});
+  win_bwd_consume<VT, kL, kWinPool, kDet>(sm, a, lv, tile, m, b, (int)threadIdx.x, BlockSync{});
+}
+
+// Deterministic mode helpers: max|x| of a tensor as a float bit pattern (non-negative floats order like
+// unsigned ints; a NaN / Inf input ends up >= 0x7f800000), and the final fixed-point -> fp32 conversion.
+template <typename T>
+__global__ void __launch_bounds__(256) msda_maxabs_kernel(const T* __restrict__ x, const size_t n, unsigned* out) {
+  unsigned mx = 0;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+    mx = max(mx, __float_as_uint(fabsf((float)x[i])));
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
+}
+__global__ void __launch_bounds__(256) msda_fixed_to_float_kernel(const long long* __restrict__ acc, float* __restrict__ out,
+                                                                  const size_t n, const unsigned* __restrict__ maxbits,
+                                                                  const int Lq, const int LP) {
+  const bool finite = maxbits[0] < 0x7f800000u && maxbits[1] < 0x7f800000u;
+  const double inv = exp2(-(double)win_det_shift(maxbits, Lq, LP));
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+    out[i] = finite ? (float)((double)acc[i] * inv) : __int_as_float(0x7fc00000);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1000,13 +1098,13 @@ msda_bwd_d32_ws_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels l
     if (role == 0) {
       if (use > 0) mbar_wait(bars + 2 + set, (use - 1) & 1);  // the consumer released the set
       if (t == 0) WIN_T(11, tph);  // producer waiting for a free buffer set
-      win_bwd_produce<VT, kL, kWinPool>(sm, a, lv, tile, m, b, t, GroupSync<1>{});
+      win_bwd_produce<VT, kL, kWinPool, false>(sm, a, lv, tile, m, b, t, GroupSync<1>{});
       if (t == 0) WIN_T(8, tph);   // produce
       if (t == 0) mbar_arrive(bars + set);
     } else {
       mbar_wait(bars + set, use & 1);
       if (t == 0) WIN_T(9, tph);   // consumer waiting for a full buffer set
-      win_bwd_consume<VT, kL, kWinPool>(sm, a, lv, tile, m, b, t, GroupSync<2>{});
+      win_bwd_consume<VT, kL, kWinPool, false>(sm, a, lv, tile, m, b, t, GroupSync<2>{});
       GroupSync<2>{}();  // every consumer thread is done with the set
       if (t == 0) WIN_T(10, tph);  // consume
 #ifdef MSDA_WIN_TIMING

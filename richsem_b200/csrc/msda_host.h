@@ -47,6 +47,11 @@ template <typename VT>
 int bwd_d32_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
                 const float* attw, float* gv, float* gl, float* ga);
 
+// deterministic variant of the window backward (large problems): canonical order inside a block, fixed-point
+// accumulation across blocks; needs 256 + 8 bytes per grad_value element of workspace
+template <typename VT>
+int bwd_d32_win_det(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
+                    const float* attw, float* gv, float* gl, float* ga, void* workspace, size_t workspace_bytes);
 // grad_value alone, by cell-sorted accumulation (msda_d32_gv.cuh); pairs with bwd_d32<VT, false>.
 template <typename VT>
 int gradvalue_d32(cudaStream_t s, const Problem& pb, const VT* go, const float* loc, const float* attw, float* gv);

@@ -38,7 +38,12 @@ int det_grad_value(cudaStream_t s, const Problem& pb, const TV* go, const float*
 
 size_t det_workspace_bytes(int batch, int spatial_size, int num_heads, int channels, int num_levels,
                            int num_query, int num_point) {
-  return deterministic_workspace_bytes(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point);
+  // the larger of the two deterministic paths: sort-by-corner ids (msda_det.cuh) and the window kernel's
+  // fixed-point accumulators (256 + 8 bytes per grad_value element, msda_launch_win.cu)
+  const size_t ids = deterministic_workspace_bytes(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point);
+  if (batch < 1 || spatial_size < 1 || num_heads < 1 || channels < 1) return ids;
+  const size_t fixed = 256 + (size_t)batch * spatial_size * num_heads * channels * 8;
+  return ids > fixed ? ids : fixed;
 }
 
 int corners_probe(cudaStream_t s, const MsdaLevels& lv, const float* loc, int32_t* corners, long long n,

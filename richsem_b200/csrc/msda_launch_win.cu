@@ -29,19 +29,22 @@ WinBwdArgs make_bwd_args(const Problem& pb, const VT* go, const VT* value, const
   a.grad_value = gv; a.grad_loc = gl; a.grad_attw = ga;
   a.order = pb.order; a.order_len = pb.order_len;
   a.S = pb.d.spatial_size; a.M = pb.d.num_heads; a.Lq = pb.d.num_query;
+  a.gv64 = nullptr; a.maxbits = nullptr;
   return a;
 }
 
-template <typename VT, int kL, int kM>
+template <typename VT, int kL, int kM, bool kDet>
 int launch_bwd_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
-                   const float* attw, float* gv, float* gl, float* ga) {
+                   const float* attw, float* gv, float* gl, float* ga, long long* gv64, const unsigned* maxbits) {
   using Cfg = WinCfg<VT, kL, kWinPoolBwd>;
-  auto kern = msda_bwd_d32_win_kernel<VT, kL, kM>;
+  auto kern = msda_bwd_d32_win_kernel<VT, kL, kM, kDet>;
   static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BWD_SMEM);
   if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_bwd_d32_win_kernel)");
   const int tiles = (pb.order_len + kWinTileQ - 1) / kWinTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
-  kern<<<grid, kWinThreads, Cfg::BWD_SMEM, s>>>(make_bwd_args(pb, go, value, loc, attw, gv, gl, ga), pb.lv);
+  WinBwdArgs a = make_bwd_args(pb, go, value, loc, attw, gv, gl, ga);
+  a.gv64 = gv64; a.maxbits = maxbits;
+  kern<<<grid, kWinThreads, Cfg::BWD_SMEM, s>>>(a, pb.lv);
   return after_launch("msda_bwd_d32_win_kernel");
 }
 
@@ -109,10 +112,45 @@ int bwd_d32_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value
     MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL
   }
-  if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_bwd_win<VT, 4, 8>(s, pb, go, value, loc, attw, gv, gl, ga);
-#define CALL(L) launch_bwd_win<VT, L, 0>(s, pb, go, value, loc, attw, gv, gl, ga)
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 4)
+    return launch_bwd_win<VT, 4, 8, false>(s, pb, go, value, loc, attw, gv, gl, ga, nullptr, nullptr);
+#define CALL(L) launch_bwd_win<VT, L, 0, false>(s, pb, go, value, loc, attw, gv, gl, ga, nullptr, nullptr)
   MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL
+}
+
+// Deterministic backward for large problems.  Workspace: [256 B header: max|grad_out| bits, max|attn_weight|
+// bits][int64 fixed-point accumulators, one per grad_value element].
+template <typename VT>
+int bwd_d32_win_det(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
+                    const float* attw, float* gv, float* gl, float* ga, void* ws, size_t ws_bytes) {
+  const size_t n_gv = (size_t)pb.d.batch * pb.d.spatial_size * pb.d.num_heads * 32;
+  const size_t need = 256 + n_gv * 8;
+  if (!ws || ws_bytes < need)
+    return fail(MSDA_ERR_WORKSPACE, "deterministic mode needs %zu workspace bytes, got %zu", need, ws_bytes);
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(MSDA_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  unsigned* maxbits = static_cast<unsigned*>(ws);
+  long long* gv64 = reinterpret_cast<long long*>(static_cast<char*>(ws) + 256);
+  int rc = check_cuda(cudaMemsetAsync(ws, 0, need, s), "workspace clear");
+  if (rc) return rc;
+  const size_t n_go = (size_t)pb.d.batch * pb.d.num_query * pb.d.num_heads * 32;
+  const size_t n_aw = (size_t)pb.d.batch * pb.d.num_query * pb.d.num_heads * pb.d.num_levels * pb.d.num_point;
+  msda_maxabs_kernel<VT><<<148 * 8, 256, 0, s>>>(go, n_go, maxbits);
+  if ((rc = after_launch("msda_maxabs_kernel(grad_out)"))) return rc;
+  msda_maxabs_kernel<float><<<148 * 8, 256, 0, s>>>(attw, n_aw, maxbits + 1);
+  if ((rc = after_launch("msda_maxabs_kernel(attn_weight)"))) return rc;
+  if (pb.d.num_heads == 8 && pb.d.num_levels == 4) {
+    rc = launch_bwd_win<VT, 4, 8, true>(s, pb, go, value, loc, attw, gv, gl, ga, gv64, maxbits);
+  } else {
+    rc = [&]() -> int {
+#define CALL(L) launch_bwd_win<VT, L, 0, true>(s, pb, go, value, loc, attw, gv, gl, ga, gv64, maxbits)
+      MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+    }();
+  }
+  if (rc) return rc;
+  msda_fixed_to_float_kernel<<<148 * 8, 256, 0, s>>>(gv64, gv, n_gv, maxbits, pb.d.num_query, pb.d.num_levels * pb.d.num_point);
+  return after_launch("msda_fixed_to_float_kernel");
 }
 
 template <typename VT>
@@ -126,6 +164,10 @@ template int gradvalue_d32<float>(cudaStream_t, const Problem&, const float*, co
 template int gradvalue_d32<__nv_bfloat16>(cudaStream_t, const Problem&, const __nv_bfloat16*, const float*, const float*,
                                           float*);
 
+template int bwd_d32_win_det<float>(cudaStream_t, const Problem&, const float*, const float*, const float*, const float*,
+                                    float*, float*, float*, void*, size_t);
+template int bwd_d32_win_det<__nv_bfloat16>(cudaStream_t, const Problem&, const __nv_bfloat16*, const __nv_bfloat16*,
+                                            const float*, const float*, float*, float*, float*, void*, size_t);
 template int fwd_d32_win<float>(cudaStream_t, const Problem&, const float*, const float*, const float*, float*);
 template int fwd_d32_win<__nv_bfloat16>(cudaStream_t, const Problem&, const __nv_bfloat16*, const float*,
                                         const float*, __nv_bfloat16*);

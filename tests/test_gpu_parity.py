@@ -213,6 +213,38 @@ def test_size_independent_properties_full_size():
     assert abs(lhs - rhs) / abs(lhs) < 1e-5
 
 
+@pytest.mark.parametrize("kind,dtype", [("E", torch.float32), ("E", torch.bfloat16), ("U", torch.float32)])
+def test_deterministic_window_backward_large_problem(kind, dtype, c_oracle):
+    """Encoder-sized problems take the window kernel in deterministic mode: canonical order inside a block,
+    fixed-point (order-independent) accumulation across blocks.  Bitwise reproducible, within 1e-4 of the
+    oracle; "U" (no locality) sends most levels through the direct path."""
+    from richsem_b200 import _capi, synthetic as syn
+
+    shapes = [(64, 84), (32, 42), (16, 21), (8, 11)]
+    i = syn.make_inputs(kind, 2, shapes, "cuda:0", seed=12, lq=None if kind == "E" else 6000, dtype=dtype)
+    if kind == "U":
+        i["loc"] = (i["loc"] * 1.3 - 0.15).contiguous()
+    args = (i["value"], i["shapes"], i["starts"], i["loc"], i["attw"], i["grad_out"], 64)
+    b = _ext().ms_deform_attn_backward
+    d1 = b(*args, _flags=_capi.FLAG_DETERMINISTIC)
+    d2 = b(*args, _flags=_capi.FLAG_DETERMINISTIC)
+    at = b(*args)
+    for x, y in zip(d1, d2):
+        assert torch.equal(x, y)
+    for x, y in zip(d1, at):
+        assert rel_err(x, y) < (BWD_TOL if dtype == torch.float32 else 1e-3)
+    if dtype == torch.float32:
+        v, loc, w, go = (i[k].cpu() for k in ("value", "loc", "attw", "grad_out"))
+        wv, wl, wa = c_oracle.backward(go, v, shapes, loc, w)
+        assert rel_err(d1[0].cpu(), wv) < BWD_TOL and rel_err(d1[1].cpu(), wl) < BWD_TOL and rel_err(d1[2].cpu(), wa) < BWD_TOL
+    # scale robustness: tiny and huge gradients keep their relative accuracy
+    for scale in (1e-12, 1e12):
+        go2 = (i["grad_out"].float() * scale).to(dtype)
+        x = b(*args[:5], go2, 64, _flags=_capi.FLAG_DETERMINISTIC)[0]
+        y = b(*args[:5], go2, 64)[0]
+        assert rel_err(x, y) < (BWD_TOL if dtype == torch.float32 else 1e-3)
+
+
 def test_deterministic_mode_is_bitwise_reproducible_and_close_to_atomic():
     from richsem_b200 import _capi, synthetic as syn
 
