@@ -177,10 +177,13 @@ def build_patch_order(shapes, starts, pad=False):
                 + (ys % PATCH) * PATCH + xs % PATCH
             parts.append(st + np.argsort(key.ravel(), kind="stable"))
         else:
-            hp, wp = (h + PATCH - 1) // PATCH * PATCH, (w + PATCH - 1) // PATCH * PATCH
+            sup = int(os.environ.get("MSDA_B200_SUPER_PATCH", "1"))  # experiment: SUPxSUP patches per super-patch
+            big = PATCH * sup
+            hp, wp = (h + big - 1) // big * big, (w + big - 1) // big * big
             ys, xs = np.meshgrid(np.arange(hp), np.arange(wp), indexing="ij")
             tok = np.where((ys < h) & (xs < w), st + ys * w + xs, -1)
-            tok = tok.reshape(hp // PATCH, PATCH, wp // PATCH, PATCH).transpose(0, 2, 1, 3).reshape(-1)
+            # (super row, sub row, y, super col, sub col, x) -> super-patch major, then 8x8 sub-patch, then pixel
+            tok = tok.reshape(hp // big, sup, PATCH, wp // big, sup, PATCH).transpose(0, 3, 1, 4, 2, 5).reshape(-1)
             parts.append(tok)
     return np.concatenate(parts).astype(np.int32)
 
@@ -197,7 +200,7 @@ def query_order(meta: LevelMeta, num_query: int, device) -> "torch.Tensor | None
             return None
         acc += h * w
     pad = os.environ.get("MSDA_B200_ORDER_PAD", "1") not in ("", "0")
-    key = (meta.shapes, str(device), pad)
+    key = (meta.shapes, str(device), pad, os.environ.get("MSDA_B200_SUPER_PATCH", "1"))
     t = _order_cache.get(key)
     if t is None:
         t = torch.from_numpy(build_patch_order(meta.shapes, meta.starts, pad=pad)).to(device)

@@ -38,7 +38,10 @@ namespace msda {
 #endif
 constexpr int kThreads = MSDA_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kTileQ = 64;  // queries per thread block
+#ifndef MSDA_TILE_Q
+#define MSDA_TILE_Q 64
+#endif
+constexpr int kTileQ = MSDA_TILE_Q;  // queries per thread block
 
 // ---- per-value-type traits ----------------------------------------------------------------
 template <typename VT>
@@ -222,8 +225,8 @@ msda_fwd_d32_kernel(const VT* __restrict__ value, const float* __restrict__ loc,
 // Against the 8-lane kernel above this halves the non-FMA instructions per sample (address
 // arithmetic, predicates, record reads) and the FMA instructions.  An L1-resident row gather sustains
 // 1.2 cycles per row with LDG.128 and 1.08 with LDG.256 (scratch/gather256.cu), but at the headline shape
-// this kernel is no faster than the 8-lane one (0.147 vs 0.142 ms): the forward is bound by L1 misses
-// (78 % hit rate; the co-resident blocks' working sets exceed L1), so it is opt-in (MSDA_FLAG_LDG256).
+// this kernel is no faster than the 8-lane one (0.147 vs 0.142 ms): the forward is co-limited by the L1
+// data path and instruction issue, so it is opt-in (MSDA_FLAG_LDG256).
 // Requires a 32-byte aligned value / out.
 // ------------------------------------------------------------------------------------------
 template <int LP>
