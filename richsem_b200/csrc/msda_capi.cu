@@ -165,7 +165,7 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
     const bool fast = !(pb.flags & MSDA_FLAG_FORCE_GENERIC) &&
                       fast_shape(sizeof(TV), channels, num_levels, num_point) && fits_int32(pb.d) &&
                       aligned(value, 16) && aligned(gv, 16) && aligned(loc, 16) && aligned(attw, 16) &&
-                      aligned(grad_out, 16) && aligned(gl, 8);
+                      aligned(grad_out, 16) && aligned(gl, 16) && aligned(ga, 16);  // 16-byte vector loads / stores / reductions
     if (fast && no_gv) return msda::bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
     // deterministic, large problem: the window kernel with canonical in-block order and fixed-point accumulation
     if (fast && det && !msda::use_split(pb) && !(pb.flags & MSDA_FLAG_NO_WINDOW))

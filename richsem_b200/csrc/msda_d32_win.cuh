@@ -4,8 +4,9 @@
 //
 // Why (measured on B200, scratch/gather_bw.cu, scratch/tma_stage.cu, scratch/smem_atomics.cu):
 //   * a gather of 128-byte rows out of L1 (LDG.128, 4 rows per warp instruction, all hits) runs at
-//     1.9 SM-cycles per row — the rate the tiled kernels (msda_d32.cuh) sit on — while the same gather
-//     out of shared memory (LDS.128) runs at 1.04 cycles per row, the 128 B/clk limit of the data pipe;
+//     1.2 SM-cycles per row with all of L1 available and 1.9 when shared memory takes most of it (the
+//     tiled kernels of msda_d32.cuh sit at 1.8), while the same gather out of shared memory (LDS.128)
+//     runs at 1.04 cycles per row, the 128 B/clk limit of the data pipe;
 //   * L2 retires scattered fp32 row reductions at 5.8 SM-cycles per row per SM (6.4 TB/s chip-wide):
 //     22.75 M of them per bs=2 encoder layer is the 455 us floor of the plain backward; shared-memory
 //     float atomics are a CAS loop (14.7 cycles per row; 5.1 with a 128-bit CAS), so merging must be
@@ -22,13 +23,15 @@
 //              Levels that do not fit stay "direct": their samples gather from global memory.
 //   forward    lane groups (8 lanes x float4 for fp32 rows, 4 lanes x 8 bf16) walk the records of their
 //              queries: one broadcast LDS.128 per point, four row reads, 16 FFMA.
-//   backward   the windowed samples are counting-sorted by cell (= pool row of corner (h0,w0)); each lane
-//              group walks a contiguous chunk of the sorted list holding the current cell's four value
-//              rows and four grad_value accumulators in registers: per sample one LDS.128 of grad_out,
-//              16 FFMA of dot products, 16 FFMA of accumulation; a cell change flushes two (adjacent
-//              cell: the other two slide over) or four accumulators with REDG.ADD.F32x4 — ~5x fewer
-//              L2 reductions than one per corner.  grad_sampling_loc / grad_attn_weight are parked in the
-//              record slots and written out coalesced at the end.
+//   backward   produce: the windowed samples are counting-sorted by cell (= pool row of corner (h0,w0)).
+//              consume: each 4-lane group (8 channels per lane) walks a contiguous chunk of the sorted list
+//              holding the current cell's four value rows and four grad_value accumulators in registers:
+//              per sample two LDS.128 of grad_out, 16 FFMA2 of dot products, 16 FFMA2 of accumulation; a
+//              cell change flushes two (adjacent cell: the other two slide over) or four accumulators with
+//              REDG.ADD.F32x4 — 4.4x fewer L2 reductions than one per corner.  grad_sampling_loc /
+//              grad_attn_weight are parked in the record slots and written out coalesced at the end.
+//              Variants of the same two halves: deterministic (canonical order inside the block, 64-bit
+//              fixed-point accumulation across blocks) and persistent / warp-specialised (opt-in).
 //
 // The arithmetic restates models/richsem/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299 (forward),
 // :87-159 (gradients); nothing of that file's thread mapping or reductions is used.
