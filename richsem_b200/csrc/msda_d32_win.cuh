@@ -144,6 +144,9 @@ struct WinCfg {
   static constexpr int OFF_SORTED = OFF_ROWOFF + ROWOFF_BYTES;
   static constexpr int INFLAG_BYTES = ((NLV * 4 * kWinTileQ + 127) / 128) * 128;
   static constexpr int BWD_SMEM = OFF_SORTED + SORTED_BYTES + 192 + INFLAG_BYTES;
+  // deterministic mode: per-warp, per-cell sample counts (16-bit) that make the sort ranks scheduling-independent
+  static constexpr int WCNT_BYTES = (kWinThreads / 32) * HIST_N * 2;
+  static constexpr int BWD_DET_SMEM = ((BWD_SMEM + 15) / 16) * 16 + WCNT_BYTES;
   static constexpr int BWD_SET_BYTES = ((BWD_SMEM + 127) / 128) * 128;   // one buffer set of the warp-specialised kernel
   static constexpr int BWD_WS_SMEM = 2 * BWD_SET_BYTES + 64;
   static_assert(kL <= 8, "per-level state is kept in 8-entry arrays");
@@ -277,8 +280,8 @@ __device__ __forceinline__ void win_decode_level(const float* __restrict__ loc, 
 // allocation, staging (cp.async left in flight), records.  Thread t decodes level (t / 64) [+4] of
 // query t % 64, so the level is warp-uniform.  kBwd additionally fills rowoff and counts the windowed
 // samples per cell (hist; rank[][] = the sample's arrival order inside its cell).
-template <typename VT, int kL, int kWinPool, bool kBwd, class Sync>
-__device__ __forceinline__ void win_front_end(const int t, const Sync sync, const VT* __restrict__ value_img, const float* __restrict__ loc,
+template <typename VT, int kL, int kWinPool, bool kBwd, bool kDetRank, class Sync>
+__device__ __forceinline__ void win_front_end(const int t, const Sync sync, unsigned short* wcnt, const VT* __restrict__ value_img, const float* __restrict__ loc,
                                               const float* __restrict__ attw, const int q, const size_t qm,
                                               const int qpf, const size_t qm_pf,
                                               const int m, const int M, const MsdaLevels& lv,
@@ -294,6 +297,9 @@ __device__ __forceinline__ void win_front_end(const int t, const Sync sync, cons
   if (kBwd) {
 #pragma unroll
     for (int k = 0; k < Cfg::SPT; ++k) hist[t + k * kWinThreads] = 0;
+  }
+  if (kDetRank) {
+    for (int i = t; i < Cfg::WCNT_BYTES / 16; i += kWinThreads) reinterpret_cast<uint4*>(wcnt)[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   sync();
 #pragma unroll
@@ -335,7 +341,22 @@ __device__ __forceinline__ void win_front_end(const int t, const Sync sync, cons
         rank[li][i] = -1;
         WIN_CHECK(base < 0 || ((code & 0xffff) + 1 <= kWinPool + 1 && (code >> 16) + 1 <= kWinPool + 1));
         WIN_CHECK(base < 0 || !pts[li][i].in || ((code >> 16) + 1 < kWinPool && (code & 0xffff) >= base));
-        if (kBwd && base >= 0 && pts[li][i].in) rank[li][i] = atomicAdd(&hist[code & 0xffff], 1);
+        if (kBwd && !kDetRank && base >= 0 && pts[li][i].in) rank[li][i] = atomicAdd(&hist[code & 0xffff], 1);
+        if (kDetRank) {
+          // scheduling-independent rank: lanes of a warp that hit the same cell are ranked in lane order on
+          // top of what the warp counted for that cell in earlier rounds; the warps' counts are turned into
+          // exclusive bases after the block barrier (win_bwd_produce)
+          const bool part = base >= 0 && pts[li][i].in;
+          const int cell = code & 0xffff;
+          const unsigned peers = __match_any_sync(0xffffffffu, part ? (unsigned)cell : (0xffff0000u | (unsigned)lane));
+          const int leader = __ffs(peers) - 1;
+          unsigned short* cnt = wcnt + (t >> 5) * Cfg::HIST_N + cell;
+          int prev = 0;
+          if (part && lane == leader) { prev = *cnt; *cnt = (unsigned short)(prev + __popc(peers)); }
+          prev = __shfl_sync(0xffffffffu, prev, leader);
+          if (part) rank[li][i] = prev + __popc(peers & ((1u << lane) - 1u));
+          __syncwarp();
+        }
         rec[ql * Cfg::REC_STRIDE + l * 4 + i] =
             make_float4(__int_as_float(code), pts[li][i].lh, pts[li][i].lw, pts[li][i].in ? pts[li][i].a : 0.f);
       }
@@ -389,7 +410,7 @@ msda_fwd_d32_win_kernel(const VT* __restrict__ value, const float* __restrict__ 
     const size_t qm_pf = ((size_t)b * Lq + (qpf >= 0 ? qpf : 0)) * M + m;
     WinPoint pts[Cfg::NLV][4];
     int rank[Cfg::NLV][4];
-    win_front_end<VT, kL, kWinPool, false>(t, BlockSync{}, value_img, loc, attw, q, qm, qpf, qm_pf, m, M, lv, pool, rec, bb, nullptr, nullptr, wa, pts, rank, tphase);
+    win_front_end<VT, kL, kWinPool, false, false>(t, BlockSync{}, nullptr, value_img, loc, attw, q, qm, qpf, qm_pf, m, M, lv, pool, rec, bb, nullptr, nullptr, wa, pts, rank, tphase);
   }
   WIN_T(1, tphase);  // allocation, staging issue, records
   cp_async_wait_all();
@@ -540,6 +561,7 @@ struct WinBwdSmem {
   int* misc;               // [0,16) warp totals [16] total [20,28) window base row per level (-1: direct)
   float* lvf;              // [0,8) (float)W_l  [8,16) (float)H_l
   unsigned char* inflag;   // per (level slot, query): bit i = point i passed the range test
+  unsigned short* wcnt;    // deterministic mode only: [warp][cell] counts, then exclusive bases over the warps
   __device__ __forceinline__ explicit WinBwdSmem(unsigned char* base)
       : pool(base),
         rec(reinterpret_cast<float4*>(base + Cfg::POOL_BYTES)),
@@ -550,7 +572,8 @@ struct WinBwdSmem {
         sorted(reinterpret_cast<unsigned short*>(base + Cfg::OFF_SORTED)),
         misc(reinterpret_cast<int*>(base + Cfg::OFF_SORTED + Cfg::SORTED_BYTES)),
         lvf(reinterpret_cast<float*>(base + Cfg::OFF_SORTED + Cfg::SORTED_BYTES) + 32),
-        inflag(base + Cfg::OFF_SORTED + Cfg::SORTED_BYTES + 192) {}
+        inflag(base + Cfg::OFF_SORTED + Cfg::SORTED_BYTES + 192),
+        wcnt(reinterpret_cast<unsigned short*>(base + ((Cfg::BWD_SMEM + 15) / 16) * 16)) {}
 };
 
 struct WinBwdArgs {
@@ -585,6 +608,11 @@ __device__ __forceinline__ float win_det_scale(const unsigned* maxbits, const in
 __device__ __forceinline__ void win_det_add(long long* p, const float v, const float scale) {
   atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__float2ll_rn(v * scale));
 }
+// Position of channel c inside a row of the fixed-point accumulator array (a private workspace, so its
+// layout is ours to choose): channel 4*chunk + i -> 8*i + chunk.  Lanes that hold the same element i of
+// consecutive chunks — which is how both the sorted pass and the direct pass distribute a row — then add
+// into consecutive accumulators, i.e. one 32-byte sector per four lanes (L2 retires atomics per sector).
+__device__ __forceinline__ int win_det_pos(const int c) { return 8 * (c & 3) + (c >> 2); }
 // 4x4 transpose over the 4 lanes of a quad (q = lane & 3): afterwards a[L] is what lane L of the quad held in
 // a[q].  Lets the four lanes of one 64-bit reduction instruction hit four CONSECUTIVE accumulators (one 32-byte
 // sector) instead of four sectors — L2 retires atomics per sector.
@@ -652,7 +680,7 @@ __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, 
   WinAlloc<kL> wa;
   WinPoint pts[Cfg::NLV][4];
   int rank[Cfg::NLV][4];
-  win_front_end<VT, kL, kWinPool, true>(t, sync, value_img, ar.loc, ar.attw, dq, dqm, qpf, qm_pf, m, M, lv, sm.pool, sm.rec,
+  win_front_end<VT, kL, kWinPool, true, kDet>(t, sync, sm.wcnt, value_img, ar.loc, ar.attw, dq, dqm, qpf, qm_pf, m, M, lv, sm.pool, sm.rec,
                                         sm.bb, sm.rowoff, sm.hist, wa, pts, rank, tphase);
 #pragma unroll
   for (int it = 0; it < GO_ITERS; ++it) {
@@ -675,6 +703,20 @@ __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, 
       if (l == t - 32) sm.misc[20 + l] = wa.base[l];
   }
   sync();  // hist complete, records visible
+  if (kDet) {
+    // per cell: the warps' counts -> exclusive bases over the warps, their sum -> hist
+    for (int c = t; c < Cfg::HIST_N; c += kWinThreads) {
+      int run = 0;
+#pragma unroll
+      for (int w = 0; w < kWinThreads / 32; ++w) {
+        const int n = sm.wcnt[w * Cfg::HIST_N + c];
+        sm.wcnt[w * Cfg::HIST_N + c] = (unsigned short)run;
+        run += n;
+      }
+      sm.hist[c] = run;
+    }
+    sync();
+  }
 
   // ---- exclusive scan of the per-cell counts, in place -----------------------------------------
   {
@@ -706,23 +748,9 @@ __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, 
         if (rank[li][i] >= 0) {
           const int code = __float_as_int(sm.rec[dql * Cfg::REC_STRIDE + l * 4 + i].x);
           WIN_CHECK(sm.hist[code & 0xffff] + rank[li][i] >= 0 && sm.hist[code & 0xffff] + rank[li][i] < sm.misc[16]);
-          sm.sorted[sm.hist[code & 0xffff] + rank[li][i]] = (unsigned short)(dql * LP + l * 4 + i);
+          const int wbase = kDet ? (int)sm.wcnt[warp * Cfg::HIST_N + (code & 0xffff)] : 0;
+          sm.sorted[sm.hist[code & 0xffff] + wbase + rank[li][i]] = (unsigned short)(dql * LP + l * 4 + i);
         }
-    }
-  }
-  if (kDet) {
-    // canonical order inside every cell: the ranks above are arrival orders of shared-memory atomics, so
-    // each cell's run of sample ids is sorted before anything is summed (runs are short: ~3 ids)
-    sync();
-    const int total = sm.misc[16];
-    for (int c = t; c < kWinPool; c += kWinThreads) {
-      const int beg = sm.hist[c], end = (c + 1 < Cfg::HIST_N) ? sm.hist[c + 1] : total;
-      for (int i = beg + 1; i < end; ++i) {
-        const unsigned short key = sm.sorted[i];
-        int k = i - 1;
-        while (k >= beg && sm.sorted[k] > key) { sm.sorted[k + 1] = sm.sorted[k]; --k; }
-        sm.sorted[k + 1] = key;
-      }
     }
   }
   cp_async_wait_all();
@@ -786,16 +814,14 @@ __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, 
       WIN_CHECK(off < 0 || (off % 32 == 0 && off / 32 < S * M));
       if (off >= 0) {
         if (kDet) {
-          // lane sj holds chunks cA, cB (4 channels each); after the quad transposes it holds element sj of
-          // every lane's chunk, so the 4 lanes of one reduction instruction cover one chunk = one 32-byte sector
-          float ta[4] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y}, tb[4] = {acc[2].x, acc[2].y, acc[3].x, acc[3].y};
-          quad_transpose4(ta, sj, gmask);
-          quad_transpose4(tb, sj, gmask);
-#pragma unroll
-          for (int L = 0; L < 4; ++L) {  // ta[L] / tb[L]: element sj of lane L's chunk a / b
-            win_det_add(gv64 + off + SL::chunk_a(sg, L) * 4 + sj, ta[L], dscale);
-            win_det_add(gv64 + off + SL::chunk_b(sg, L) * 4 + sj, tb[L], dscale);
-          }
+          // accumulator layout (win_det_pos): channel 4*chunk + i sits at 8*i + chunk, so the four lanes of
+          // one reduction instruction (same i, chunks sj .. sj+3) hit one 32-byte sector
+          long long* pa = gv64 + off + SL::chunk_a(sg, sj);
+          long long* pb = gv64 + off + SL::chunk_b(sg, sj);
+          win_det_add(pa, acc[0].x, dscale); win_det_add(pa + 8, acc[0].y, dscale);
+          win_det_add(pa + 16, acc[1].x, dscale); win_det_add(pa + 24, acc[1].y, dscale);
+          win_det_add(pb, acc[2].x, dscale); win_det_add(pb + 8, acc[2].y, dscale);
+          win_det_add(pb + 16, acc[3].x, dscale); win_det_add(pb + 24, acc[3].y, dscale);
         } else {
           red_add_f4(gvalue_a + off, acc[0].x, acc[0].y, acc[1].x, acc[1].y);
           red_add_f4(gvalue_b + off, acc[2].x, acc[2].y, acc[3].x, acc[3].y);
@@ -939,15 +965,9 @@ __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, 
               RT::load(value_j + o, v);
               const float tt = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
               if (kDet) {
-                const unsigned qmask = 0xfu << (lane & ~3);
 #pragma unroll
-                for (int c = 0; c < C; c += 4) {
-                  float tq[4] = {tt * go[c], tt * go[c + 1], tt * go[c + 2], tt * go[c + 3]};
-                  quad_transpose4(tq, j & 3, qmask);
-#pragma unroll
-                  for (int L = 0; L < 4; ++L)  // lane L of the quad held channels (j & ~3 | L) * C + c .. + 3
-                    win_det_add(gv64 + o + ((j & ~3) + L) * C + c + (j & 3), tq[L], dscale);
-                }
+                for (int c = 0; c < C; ++c)  // lane j holds channels j*C + c: chunk (j*C + c) / 4, element (j*C + c) % 4
+                  win_det_add(gv64 + o + win_det_pos(j * C + c), tt * go[c], dscale);
               } else {
 #pragma unroll
                 for (int c = 0; c < C; c += 4)
@@ -1025,12 +1045,28 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
 // Deterministic mode helpers: max|x| of a tensor as a float bit pattern (non-negative floats order like
 // unsigned ints; a NaN / Inf input ends up >= 0x7f800000), and the final fixed-point -> fp32 conversion.
 template <typename T>
-__global__ void __launch_bounds__(256) msda_maxabs_kernel(const T* __restrict__ x, const size_t n, unsigned* out) {
-  unsigned mx = 0;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
-    mx = max(mx, __float_as_uint(fabsf((float)x[i])));
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
+__global__ void __launch_bounds__(256)
+msda_maxabs_kernel(const T* __restrict__ go, const size_t n_go, const float* __restrict__ aw, const size_t n_aw, unsigned* out) {
+  // 16-byte loads; both tensors have a multiple of 16 bytes (32 channels / 4 points per row)
+  constexpr int EPV = 16 / (int)sizeof(T);
+  const size_t tid = (size_t)blockIdx.x * 256 + threadIdx.x, nth = (size_t)gridDim.x * 256;
+  unsigned m_go = 0, m_aw = 0;
+  for (size_t i = tid; i < n_go / EPV; i += nth) {
+    float v[EPV];
+    RowTraits<T>::load_stream(go + i * EPV, v);
+#pragma unroll
+    for (int c = 0; c < EPV; ++c) m_go = max(m_go, __float_as_uint(fabsf(v[c])));
+  }
+  for (size_t i = tid; i < n_aw / 4; i += nth) {
+    const float4 v = ld_stream_f4(aw + i * 4);
+    m_aw = max(max(m_aw, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+  }
+  m_go = __reduce_max_sync(0xffffffffu, m_go);
+  m_aw = __reduce_max_sync(0xffffffffu, m_aw);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, m_go);
+    atomicMax(out + 1, m_aw);
+  }
 }
 __global__ void __launch_bounds__(256) msda_fixed_to_float_kernel(const long long* __restrict__ acc, float* __restrict__ out,
                                                                   const size_t n, const unsigned* __restrict__ maxbits,
@@ -1038,7 +1074,7 @@ __global__ void __launch_bounds__(256) msda_fixed_to_float_kernel(const long lon
   const bool finite = maxbits[0] < 0x7f800000u && maxbits[1] < 0x7f800000u;
   const double inv = exp2(-(double)win_det_shift(maxbits, Lq, LP));
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
-    out[i] = finite ? (float)((double)acc[i] * inv) : __int_as_float(0x7fc00000);
+    out[i] = finite ? (float)((double)acc[(i & ~(size_t)31) + win_det_pos((int)(i & 31))] * inv) : __int_as_float(0x7fc00000);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -38,13 +38,14 @@ int launch_bwd_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* va
                    const float* attw, float* gv, float* gl, float* ga, long long* gv64, const unsigned* maxbits) {
   using Cfg = WinCfg<VT, kL, kWinPoolBwd>;
   auto kern = msda_bwd_d32_win_kernel<VT, kL, kM, kDet>;
-  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BWD_SMEM);
+  constexpr int kSmem = kDet ? Cfg::BWD_DET_SMEM : Cfg::BWD_SMEM;
+  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_bwd_d32_win_kernel)");
   const int tiles = (pb.order_len + kWinTileQ - 1) / kWinTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
   WinBwdArgs a = make_bwd_args(pb, go, value, loc, attw, gv, gl, ga);
   a.gv64 = gv64; a.maxbits = maxbits;
-  kern<<<grid, kWinThreads, Cfg::BWD_SMEM, s>>>(a, pb.lv);
+  kern<<<grid, kWinThreads, kSmem, s>>>(a, pb.lv);
   return after_launch("msda_bwd_d32_win_kernel");
 }
 
@@ -135,10 +136,8 @@ int bwd_d32_win_det(cudaStream_t s, const Problem& pb, const VT* go, const VT* v
   if (rc) return rc;
   const size_t n_go = (size_t)pb.d.batch * pb.d.num_query * pb.d.num_heads * 32;
   const size_t n_aw = (size_t)pb.d.batch * pb.d.num_query * pb.d.num_heads * pb.d.num_levels * pb.d.num_point;
-  msda_maxabs_kernel<VT><<<148 * 8, 256, 0, s>>>(go, n_go, maxbits);
-  if ((rc = after_launch("msda_maxabs_kernel(grad_out)"))) return rc;
-  msda_maxabs_kernel<float><<<148 * 8, 256, 0, s>>>(attw, n_aw, maxbits + 1);
-  if ((rc = after_launch("msda_maxabs_kernel(attn_weight)"))) return rc;
+  msda_maxabs_kernel<VT><<<148 * 8, 256, 0, s>>>(go, n_go, attw, n_aw, maxbits);
+  if ((rc = after_launch("msda_maxabs_kernel"))) return rc;
   if (pb.d.num_heads == 8 && pb.d.num_levels == 4) {
     rc = launch_bwd_win<VT, 4, 8, true>(s, pb, go, value, loc, attw, gv, gl, ga, gv64, maxbits);
   } else {
