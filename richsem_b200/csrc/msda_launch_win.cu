@@ -3,16 +3,33 @@
 #include "msda_d32_win.cuh"
 #include "msda_d32_gv.cuh"
 
+#include <atomic>
+
 namespace msda {
 namespace {
+
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute belongs to (function, device), so it is
+// set once per device the kernel is launched on (one process may drive several GPUs), not once per process.
+template <auto kKern>
+int ensure_dynamic_smem(int bytes, const char* what) {
+  static std::atomic<unsigned long long> done{0};  // one instance per kernel (the function is the template argument)
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return check_cuda(e, "cudaGetDevice");
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return MSDA_OK;
+  e = cudaFuncSetAttribute(kKern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return check_cuda(e, what);
+  done.fetch_or(bit, std::memory_order_release);
+  return MSDA_OK;
+}
 
 template <typename VT, int kL, int kM>
 int launch_fwd_win(cudaStream_t s, const Problem& pb, const VT* value, const float* loc,
                    const float* attw, VT* out) {
   using Cfg = WinCfg<VT, kL, kWinPoolFwd>;
-  auto kern = msda_fwd_d32_win_kernel<VT, kL, kM>;
-  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::FWD_SMEM);
-  if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_fwd_d32_win_kernel)");
+  constexpr auto kern = msda_fwd_d32_win_kernel<VT, kL, kM>;
+  if (int rc = ensure_dynamic_smem<kern>(Cfg::FWD_SMEM, "cudaFuncSetAttribute(msda_fwd_d32_win_kernel)")) return rc;
   const int tiles = (pb.order_len + kWinTileQ - 1) / kWinTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
   kern<<<grid, kWinThreads, Cfg::FWD_SMEM, s>>>(value, loc, attw, out, pb.order, pb.order_len, pb.lv,
@@ -37,10 +54,9 @@ template <typename VT, int kL, int kM, bool kDet>
 int launch_bwd_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
                    const float* attw, float* gv, float* gl, float* ga, long long* gv64, const unsigned* maxbits) {
   using Cfg = WinCfg<VT, kL, kWinPoolBwd>;
-  auto kern = msda_bwd_d32_win_kernel<VT, kL, kM, kDet>;
+  constexpr auto kern = msda_bwd_d32_win_kernel<VT, kL, kM, kDet>;
   constexpr int kSmem = kDet ? Cfg::BWD_DET_SMEM : Cfg::BWD_SMEM;
-  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-  if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_bwd_d32_win_kernel)");
+  if (int rc = ensure_dynamic_smem<kern>(kSmem, "cudaFuncSetAttribute(msda_bwd_d32_win_kernel)")) return rc;
   const int tiles = (pb.order_len + kWinTileQ - 1) / kWinTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
   WinBwdArgs a = make_bwd_args(pb, go, value, loc, attw, gv, gl, ga);
@@ -54,9 +70,8 @@ template <typename VT, int kL, int kM>
 int launch_bwd_ws(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
                   const float* attw, float* gv, float* gl, float* ga) {
   using Cfg = WinCfg<VT, kL, kWinPoolBwd>;
-  auto kern = msda_bwd_d32_ws_kernel<VT, kL, kM>;
-  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BWD_WS_SMEM);
-  if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_bwd_d32_ws_kernel)");
+  constexpr auto kern = msda_bwd_d32_ws_kernel<VT, kL, kM>;
+  if (int rc = ensure_dynamic_smem<kern>(Cfg::BWD_WS_SMEM, "cudaFuncSetAttribute(msda_bwd_d32_ws_kernel)")) return rc;
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -72,9 +87,8 @@ int launch_bwd_ws(cudaStream_t s, const Problem& pb, const VT* go, const VT* val
 template <typename VT, int kL, int kM>
 int launch_gradvalue(cudaStream_t s, const Problem& pb, const VT* go, const float* loc, const float* attw, float* gv) {
   using Cfg = GvCfg<kL>;
-  auto kern = msda_gradvalue_d32_kernel<VT, kL, kM>;
-  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-  if (attr != cudaSuccess) return check_cuda(attr, "cudaFuncSetAttribute(msda_gradvalue_d32_kernel)");
+  constexpr auto kern = msda_gradvalue_d32_kernel<VT, kL, kM>;
+  if (int rc = ensure_dynamic_smem<kern>(Cfg::SMEM_BYTES, "cudaFuncSetAttribute(msda_gradvalue_d32_kernel)")) return rc;
   const int tiles = (pb.order_len + kWinTileQ - 1) / kWinTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
   kern<<<grid, kWinThreads, Cfg::SMEM_BYTES, s>>>(go, loc, attw, gv, pb.order, pb.order_len, pb.lv,
