@@ -139,6 +139,42 @@ int msda_backward_bf16(msda_stream_t stream, const uint16_t* grad_out, const uin
                        int num_query, int num_point, float* grad_value, float* grad_sampling_loc,
                        float* grad_attn_weight, const msda_opts* opts);
 
+/* ---- fused prologue ---------------------------------
+ * The module computes sampling locations and attention weights from the raw outputs of two Linear layers
+ * (models/richsem/ops/modules/ms_deform_attn.py:98-111: softmax over L*P, reference point + normalised
+ * offset) in five elementwise PyTorch kernels around the op.  These entry points take the RAW tensors
+ *   sampling_offsets  [batch, num_query, num_heads, num_levels, num_point, 2]
+ *   attn_logits       [batch, num_query, num_heads, num_levels * num_point]
+ *   reference_points  [batch, num_query, num_levels, ref_dim]      ref_dim 2: points, 4: (cx, cy, w, h) boxes
+ * and do that arithmetic inside the kernels' decode step (same operations in the same order, so corner
+ * indices are unchanged); the backward returns the gradients of the raw tensors (no gradient for
+ * reference_points).  Implemented for large head_dim-32 / 4-point problems with the default kernels;
+ * otherwise MSDA_ERR_UNSUPPORTED and the caller uses the unfused entry points. */
+int msda_forward_fused_f32(msda_stream_t stream, const float* value, const int64_t* spatial_shapes,
+                           const int64_t* level_start_index, const float* sampling_offsets,
+                           const float* attn_logits, const float* reference_points, int ref_dim, int batch,
+                           int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                           int num_point, float* out, const msda_opts* opts);
+int msda_forward_fused_bf16(msda_stream_t stream, const uint16_t* value, const int64_t* spatial_shapes,
+                            const int64_t* level_start_index, const float* sampling_offsets,
+                            const float* attn_logits, const float* reference_points, int ref_dim, int batch,
+                            int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                            int num_point, uint16_t* out, const msda_opts* opts);
+int msda_backward_fused_f32(msda_stream_t stream, const float* grad_out, const float* value,
+                            const int64_t* spatial_shapes, const int64_t* level_start_index,
+                            const float* sampling_offsets, const float* attn_logits,
+                            const float* reference_points, int ref_dim, int batch, int spatial_size,
+                            int num_heads, int channels, int num_levels, int num_query, int num_point,
+                            float* grad_value, float* grad_sampling_offsets, float* grad_attn_logits,
+                            const msda_opts* opts);
+int msda_backward_fused_bf16(msda_stream_t stream, const uint16_t* grad_out, const uint16_t* value,
+                             const int64_t* spatial_shapes, const int64_t* level_start_index,
+                             const float* sampling_offsets, const float* attn_logits,
+                             const float* reference_points, int ref_dim, int batch, int spatial_size,
+                             int num_heads, int channels, int num_levels, int num_query, int num_point,
+                             float* grad_value, float* grad_sampling_offsets, float* grad_attn_logits,
+                             const msda_opts* opts);
+
 /* ---- index contract probe --------------------------------------------------
  * Writes, for every sample (b,q,m,l,p), the four bilinear corner token indices
  * (level_start_index[l] + h*W_l + w, i.e. an index into the spatial_size axis)

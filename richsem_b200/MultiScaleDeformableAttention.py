@@ -181,6 +181,78 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     return [grad_value, grad_loc, grad_attw]
 
 
+# --------------------------------------------------------------------------------------------
+# Fused prologue: the module's softmax and sampling-location arithmetic
+# (/root/reference/models/richsem/ops/modules/ms_deform_attn.py:98-111) done inside the kernels.
+# --------------------------------------------------------------------------------------------
+_FWD_FUSED = {k: getattr(_capi.lib, "msda_forward_fused_" + k) for k in ("f32", "bf16")}
+_BWD_FUSED = {k: getattr(_capi.lib, "msda_backward_fused_" + k) for k in ("f32", "bf16")}
+
+
+def fused_prologue_supported(value, num_levels, num_query, num_point) -> bool:
+    """True when the library has fused-prologue kernels for this problem: CUDA fp32 / bf16 value, head_dim 32,
+    4 points, at most 6 levels, more than 65,536 (query, head) pairs, default (non-deterministic) mode."""
+    return (value.is_cuda and value.dtype in (torch.float32, torch.bfloat16) and value.dim() == 4 and value.shape[3] == 32
+            and num_point == 4 and 1 <= num_levels <= 6 and value.shape[0] * num_query * value.shape[2] > 65536
+            and not is_deterministic())
+
+
+def _fused_args(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits, im2col_step):
+    named = (("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("reference_points", reference_points), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits))
+    _check_inputs(named)
+    _require(reference_points.dim() == 4 and reference_points.shape[-1] in (2, 4),
+             "reference_points must be (N, Lq, L, 2) or (N, Lq, L, 4)")
+    n, lq, nl, ref_dim = reference_points.shape
+    _require(sampling_offsets.dim() == 6, "sampling_offsets must be (N, Lq, M, L, P, 2)")
+    npt = sampling_offsets.shape[4]
+    dims = _dims(value, spatial_shapes, sampling_offsets, attn_logits.view(n, lq, value.shape[2], nl, npt), im2col_step)
+    _require(reference_points.dtype == torch.float32 and sampling_offsets.dtype == torch.float32
+             and attn_logits.dtype == torch.float32, "reference_points / sampling_offsets / attn_logits must be float32")
+    return dims, ref_dim
+
+
+def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                 attn_logits, im2col_step, _flags: int = 0):
+    """out (N, Lq, M*D) from the RAW sampling offsets (N, Lq, M, L, P, 2) and attention logits (N, Lq, M, L*P)."""
+    (n, s, m, d, nl, lq, npt), ref_dim = _fused_args(value, spatial_shapes, level_start_index, reference_points,
+                                                     sampling_offsets, attn_logits, im2col_step)
+    sfx = _SUFFIX[value.dtype]
+    meta = _capi.level_meta(spatial_shapes, level_start_index)
+    out = torch.empty((n, lq, m * d), dtype=value.dtype, device=value.device)
+    opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=_flags)
+    with _on_device(value.device):
+        rc = _FWD_FUSED[sfx](
+            _stream(value.device), value.data_ptr(), _dev_ptr(spatial_shapes), _dev_ptr(level_start_index),
+            sampling_offsets.data_ptr(), attn_logits.data_ptr(), reference_points.data_ptr(), ref_dim, n, s, m, d, nl, lq,
+            npt, out.data_ptr(), opts)
+    _capi.check(rc, "msda_forward_fused_" + sfx)
+    return out
+
+
+def ms_deform_attn_backward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                  attn_logits, grad_output, im2col_step, _flags: int = 0):
+    """[grad_value, grad_sampling_offsets, grad_attn_logits]; no gradient for reference_points."""
+    (n, s, m, d, nl, lq, npt), ref_dim = _fused_args(value, spatial_shapes, level_start_index, reference_points,
+                                                     sampling_offsets, attn_logits, im2col_step)
+    sfx = _SUFFIX[value.dtype]
+    _require(grad_output.is_contiguous() and grad_output.dtype == value.dtype and grad_output.numel() == n * lq * m * d,
+             "grad_output must be contiguous, with value's dtype and shape (N, Lq, M*D)")
+    meta = _capi.level_meta(spatial_shapes, level_start_index)
+    grad_value = torch.empty(value.shape, dtype=torch.float32, device=value.device)  # zero-filled by the library
+    grad_offsets = torch.empty_like(sampling_offsets)
+    grad_logits = torch.empty_like(attn_logits)
+    opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=_flags)
+    with _on_device(value.device):
+        rc = _BWD_FUSED[sfx](
+            _stream(value.device), grad_output.data_ptr(), value.data_ptr(), _dev_ptr(spatial_shapes),
+            _dev_ptr(level_start_index), sampling_offsets.data_ptr(), attn_logits.data_ptr(),
+            reference_points.data_ptr(), ref_dim, n, s, m, d, nl, lq, npt, grad_value.data_ptr(),
+            grad_offsets.data_ptr(), grad_logits.data_ptr(), opts)
+    _capi.check(rc, "msda_backward_fused_" + sfx)
+    return [grad_value, grad_offsets, grad_logits]
+
+
 def debug_corners(spatial_shapes, level_start_index, sampling_loc, _flags: int = 0):
     """int32 (N,Lq,M,L,P,4) bilinear corner token indices as the fp32/bf16 kernels compute them
     (-1 = contributes nothing).  Test hook for the bit-exact index contract."""

@@ -17,6 +17,7 @@ import torch
 _LIB_PATH = Path(os.environ.get("MSDA_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libmsda_b200.so")
 
 MSDA_OK = 0
+MSDA_ERR_UNSUPPORTED = 2
 MSDA_ABI_VERSION = 1
 FLAG_DETERMINISTIC = 0x1
 FLAG_GRAD_VALUE_PREZEROED = 0x2
@@ -69,6 +70,13 @@ def _load():
         f.argtypes, f.restype = fwd, _i
         b = getattr(lib, f"msda_backward_{sfx}")
         b.argtypes, b.restype = bwd, _i
+    fwd_fused = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, opts_p]
+    bwd_fused = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, opts_p]
+    for sfx in ("f32", "bf16"):
+        f = getattr(lib, f"msda_forward_fused_{sfx}")
+        f.argtypes, f.restype = fwd_fused, _i
+        b = getattr(lib, f"msda_backward_fused_{sfx}")
+        b.argtypes, b.restype = bwd_fused, _i
     lib.msda_debug_corners_f32.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, opts_p]
     lib.msda_debug_corners_f32.restype = _i
     lib.msda_backward_workspace_bytes.argtypes = [_i] * 7

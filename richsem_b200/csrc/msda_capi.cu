@@ -89,6 +89,7 @@ int make_problem(cudaStream_t stream, const int64_t* shapes, const int64_t* star
     return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_opts.struct_size=%u, library expects %zu",
                 opts->struct_size, sizeof(msda_opts));
   pb->d = MsdaDims{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  pb->fz = MsdaFused{nullptr, 0};
   pb->flags = opt_flags(opts);
   pb->order = opts ? opts->query_order : nullptr;
   pb->order_len = pb->order ? opts->query_order_len : num_query;
@@ -198,9 +199,93 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
   return msda::bwd_generic<TV, TA>(s, pb, !no_gv, grad_out, value, loc, attw, gv, gl, ga);
 }
 
+// ---- fused prologue: large D=32 problems only, default kernels only ----------------------
+bool fused_supported(const Problem& pb, int dtype_bytes) {
+  const uint32_t bad = MSDA_FLAG_DETERMINISTIC | MSDA_FLAG_FORCE_GENERIC | MSDA_FLAG_NO_WINDOW | MSDA_FLAG_WINDOW_FWD |
+                       MSDA_FLAG_LDG256 | MSDA_FLAG_BWD_HALVES | MSDA_FLAG_BWD_WS | MSDA_FLAG_NO_GRAD_VALUE;
+  return !(pb.flags & bad) && fast_shape(dtype_bytes, pb.d.channels, pb.d.num_levels, pb.d.num_point) &&
+         fits_int32(pb.d) && !msda::use_split(pb) && pb.d.batch > 0 && pb.d.num_query > 0;
+}
+
+template <typename TV>
+int forward_fused_impl(cudaStream_t s, const TV* value, const int64_t* shapes, const int64_t* start,
+                       const float* offsets, const float* logits, const float* ref, int ref_dim, int batch,
+                       int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                       TV* out, const msda_opts* opts) {
+  if (!value || !offsets || !logits || !ref || !out) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  if (ref_dim != 2 && ref_dim != 4) return fail(MSDA_ERR_INVALID_ARGUMENT, "reference_points last dim must be 2 or 4, got %d", ref_dim);
+  Problem pb;
+  int rc = make_problem(s, shapes, start, batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, opts, &pb);
+  if (rc != MSDA_OK) return rc;
+  if (!fused_supported(pb, sizeof(TV)) || !aligned(value, 16) || !aligned(offsets, 16) || !aligned(logits, 16) || !aligned(out, 16))
+    return fail(MSDA_ERR_UNSUPPORTED, "no fused-prologue kernel for this problem (needs a large D=32, P=4 problem and default flags)");
+  pb.fz = MsdaFused{ref, ref_dim};
+  return msda::fwd_d32<TV>(s, pb, value, offsets, logits, out);
+}
+
+template <typename TV>
+int backward_fused_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int64_t* shapes, const int64_t* start,
+                        const float* offsets, const float* logits, const float* ref, int ref_dim, int batch,
+                        int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                        float* gv, float* g_offsets, float* g_logits, const msda_opts* opts) {
+  if (!grad_out || !value || !offsets || !logits || !ref || !gv || !g_offsets || !g_logits)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  if (ref_dim != 2 && ref_dim != 4) return fail(MSDA_ERR_INVALID_ARGUMENT, "reference_points last dim must be 2 or 4, got %d", ref_dim);
+  Problem pb;
+  int rc = make_problem(s, shapes, start, batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, opts, &pb);
+  if (rc != MSDA_OK) return rc;
+  if (!fused_supported(pb, sizeof(TV)) || !aligned(value, 16) || !aligned(gv, 16) || !aligned(offsets, 16) ||
+      !aligned(logits, 16) || !aligned(grad_out, 16) || !aligned(g_offsets, 16) || !aligned(g_logits, 16))
+    return fail(MSDA_ERR_UNSUPPORTED, "no fused-prologue kernel for this problem (needs a large D=32, P=4 problem and default flags)");
+  pb.fz = MsdaFused{ref, ref_dim};
+  if (!(pb.flags & MSDA_FLAG_GRAD_VALUE_PREZEROED)) {
+    const size_t gv_bytes = (size_t)batch * spatial_size * num_heads * channels * sizeof(float);
+    if ((rc = check_cuda(cudaMemsetAsync(gv, 0, gv_bytes, s), "zero-fill of grad_value"))) return rc;
+  }
+  return msda::bwd_d32_win<TV>(s, pb, grad_out, value, offsets, logits, gv, g_offsets, g_logits);
+}
+
 }  // namespace
 
 extern "C" {
+
+int msda_forward_fused_f32(msda_stream_t stream, const float* value, const int64_t* spatial_shapes,
+                           const int64_t* level_start_index, const float* sampling_offsets, const float* attn_logits,
+                           const float* reference_points, int ref_dim, int batch, int spatial_size, int num_heads,
+                           int channels, int num_levels, int num_query, int num_point, float* out, const msda_opts* opts) {
+  return forward_fused_impl<float>((cudaStream_t)stream, value, spatial_shapes, level_start_index, sampling_offsets,
+                                   attn_logits, reference_points, ref_dim, batch, spatial_size, num_heads, channels,
+                                   num_levels, num_query, num_point, out, opts);
+}
+int msda_forward_fused_bf16(msda_stream_t stream, const uint16_t* value, const int64_t* spatial_shapes,
+                            const int64_t* level_start_index, const float* sampling_offsets, const float* attn_logits,
+                            const float* reference_points, int ref_dim, int batch, int spatial_size, int num_heads,
+                            int channels, int num_levels, int num_query, int num_point, uint16_t* out, const msda_opts* opts) {
+  return forward_fused_impl<__nv_bfloat16>((cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(value), spatial_shapes,
+                                           level_start_index, sampling_offsets, attn_logits, reference_points, ref_dim, batch,
+                                           spatial_size, num_heads, channels, num_levels, num_query, num_point,
+                                           reinterpret_cast<__nv_bfloat16*>(out), opts);
+}
+int msda_backward_fused_f32(msda_stream_t stream, const float* grad_out, const float* value, const int64_t* spatial_shapes,
+                            const int64_t* level_start_index, const float* sampling_offsets, const float* attn_logits,
+                            const float* reference_points, int ref_dim, int batch, int spatial_size, int num_heads,
+                            int channels, int num_levels, int num_query, int num_point, float* grad_value,
+                            float* grad_sampling_offsets, float* grad_attn_logits, const msda_opts* opts) {
+  return backward_fused_impl<float>((cudaStream_t)stream, grad_out, value, spatial_shapes, level_start_index, sampling_offsets,
+                                    attn_logits, reference_points, ref_dim, batch, spatial_size, num_heads, channels, num_levels,
+                                    num_query, num_point, grad_value, grad_sampling_offsets, grad_attn_logits, opts);
+}
+int msda_backward_fused_bf16(msda_stream_t stream, const uint16_t* grad_out, const uint16_t* value,
+                             const int64_t* spatial_shapes, const int64_t* level_start_index, const float* sampling_offsets,
+                             const float* attn_logits, const float* reference_points, int ref_dim, int batch,
+                             int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                             float* grad_value, float* grad_sampling_offsets, float* grad_attn_logits, const msda_opts* opts) {
+  return backward_fused_impl<__nv_bfloat16>((cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(grad_out),
+                                            reinterpret_cast<const __nv_bfloat16*>(value), spatial_shapes, level_start_index,
+                                            sampling_offsets, attn_logits, reference_points, ref_dim, batch, spatial_size,
+                                            num_heads, channels, num_levels, num_query, num_point, grad_value,
+                                            grad_sampling_offsets, grad_attn_logits, opts);
+}
 
 int msda_forward_f32(msda_stream_t stream, const float* value, const int64_t* spatial_shapes,
                      const int64_t* level_start_index, const float* sampling_loc,

@@ -23,6 +23,28 @@ struct MsdaLevels {
   int coord_fma;  // MSDA_FLAG_COORDS_FMA: pixel coordinate as one fused multiply-add (see msda_pix)
 };
 
+// Fused prologue (reference: models/richsem/ops/modules/ms_deform_attn.py:98-111).
+// ref_dim == 0: the kernel's `loc` / `attw` arguments are sampling locations and attention weights (the
+// reference op).  ref_dim == 2 | 4: they are the RAW outputs of the module's sampling_offsets / attention_weights
+// Linear layers, and the kernel itself applies the softmax over the L*P logits of a (query, head) and
+//   ref_dim 2:  loc = ref[l] + offset / (W_l, H_l)                       (ms_deform_attn.py:102-105)
+//   ref_dim 4:  loc = ref[l].xy + offset / P * ref[l].wh * 0.5           (ms_deform_attn.py:106-108)
+// with `ref` = reference_points [N, Lq, L, ref_dim]; the backward then returns the gradients of the raw tensors.
+struct MsdaFused {
+  const float* ref;
+  int ref_dim;
+};
+
+// Sampling location of one point from its raw offset (same operations, same order as the module's PyTorch
+// expression, so the coordinates — and with them the corner indices — are bit-identical to the unfused path).
+__device__ __forceinline__ float2 msda_fused_location(const MsdaFused fz, const size_t bq, const int num_levels,
+                                                      const int l, const int num_point, const int H, const int W,
+                                                      const float2 off) {
+  const float* r = fz.ref + (bq * num_levels + l) * fz.ref_dim;
+  if (fz.ref_dim == 2) return make_float2(r[0] + off.x / (float)W, r[1] + off.y / (float)H);
+  return make_float2(r[0] + off.x / (float)num_point * r[2] * 0.5f, r[1] + off.y / (float)num_point * r[3] * 0.5f);
+}
+
 struct MsdaDims {
   int batch, spatial_size, num_heads, channels, num_levels, num_query, num_point;
 };

@@ -111,19 +111,54 @@ template <int G, int kL, int kP>
 __device__ __forceinline__ void d32_decode_points(const float* __restrict__ loc,
                                                   const float* __restrict__ attw, const size_t qm,
                                                   const int j, const int m, const int M,
-                                                  const MsdaLevels& lv, float4* rec) {
-  constexpr int LP = kL * kP;
+                                                  const MsdaLevels& lv, float4* rec,
+                                                  const MsdaFused fz = MsdaFused{nullptr, 0}, const size_t bq = 0,
+                                                  const unsigned gmask = 0xffffffffu) {
+  constexpr int LP = kL * kP, KPTS = (LP + G - 1) / G;
+  float2 xy[KPTS];
+  float a[KPTS];
 #pragma unroll
-  for (int k = 0; k < (LP + G - 1) / G; ++k) {
+  for (int k = 0; k < KPTS; ++k) {
+    const int p = j + G * k;
+    xy[k] = make_float2(0.f, 0.f);
+    a[k] = 0.f;
+    if (p < LP) {
+      xy[k] = ld_stream_f2(loc + (qm * LP + p) * 2);
+      a[k] = ld_stream_f1(attw + qm * LP + p);
+    }
+  }
+  if (fz.ref_dim) {
+    // fused prologue: softmax over the (query, head)'s L*P logits, spread over the group's G lanes
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < KPTS; ++k)
+      if (j + G * k < LP) mx = fmaxf(mx, a[k]);
+#pragma unroll
+    for (int s = G / 2; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, s));
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < KPTS; ++k) {
+      a[k] = (j + G * k < LP) ? __expf(a[k] - mx) : 0.f;
+      sum += a[k];
+    }
+#pragma unroll
+    for (int s = G / 2; s >= 1; s >>= 1) sum += __shfl_xor_sync(gmask, sum, s);
+#pragma unroll
+    for (int k = 0; k < KPTS; ++k) {
+      const int p = j + G * k;
+      a[k] = a[k] / sum;
+      if (p < LP) xy[k] = msda_fused_location(fz, bq, kL, p / kP, kP, lv.H[p / kP], lv.W[p / kP], xy[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KPTS; ++k) {
     const int p = j + G * k;
     if (p < LP) {
       const int l = p / kP;
-      const float2 xy = ld_stream_f2(loc + (qm * LP + p) * 2);
-      const float a = ld_stream_f1(attw + qm * LP + p);
       const int W = lv.W[l];
       int tok[4];
       float lh, lw;
-      const bool in = msda_sample_geom(xy.x, xy.y, lv.H[l], W, lv.start[l], tok, lh, lw, lv.coord_fma != 0);
+      const bool in = msda_sample_geom(xy[k].x, xy[k].y, lv.H[l], W, lv.start[l], tok, lh, lw, lv.coord_fma != 0);
       int base = 0, mask = 0;
       if (in) {
         // token of (h0, w0), valid or not: recover it from whichever corner exists
@@ -131,7 +166,7 @@ __device__ __forceinline__ void d32_decode_points(const float* __restrict__ loc,
         mask = (tok[0] >= 0) | ((tok[1] >= 0) << 1) | ((tok[2] >= 0) << 2) | ((tok[3] >= 0) << 3);
         base = mask ? (t00 * M + m) * 32 : 0;
       }
-      rec[p] = make_float4(__int_as_float(base | mask), lh, lw, a);
+      rec[p] = make_float4(__int_as_float(base | mask), lh, lw, a[k]);
     }
   }
 }
@@ -144,7 +179,8 @@ __global__ void __launch_bounds__(kThreads)
 msda_fwd_d32_kernel(const VT* __restrict__ value, const float* __restrict__ loc,
                     const float* __restrict__ attw, VT* __restrict__ out,
                     const int* __restrict__ order, const int order_len,
-                    const __grid_constant__ MsdaLevels lv, const int S, const int M_rt, const int Lq) {
+                    const __grid_constant__ MsdaLevels lv, const int S, const int M_rt, const int Lq,
+                    const MsdaFused fz) {
   constexpr int LP = kL * kP;
   using Cfg = D32Cfg<VT, LP>;
   using RT = RowTraits<VT>;
@@ -170,7 +206,9 @@ msda_fwd_d32_kernel(const VT* __restrict__ value, const float* __restrict__ loc,
     const bool active = q >= 0;
     const size_t qm = ((size_t)b * Lq + (active ? q : 0)) * M + m;
 
-    if (active) d32_decode_points<G, kL, kP>(loc, attw, qm, j, m, M, lv, rec);
+    if (active)
+      d32_decode_points<G, kL, kP>(loc, attw, qm, j, m, M, lv, rec, fz, (size_t)b * Lq + q,
+                                   ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (g * G));
     __syncwarp();
 
     if (active) {

@@ -105,7 +105,7 @@ msda_gradvalue_d32_kernel(const VT* __restrict__ grad_out, const float* __restri
 #pragma unroll
     for (int i = 0; i < 4; ++i) pts[li][i] = WinPoint{0, 0, 0.f, 0.f, 0.f, false};
     if (l < kL) {
-      if (dq >= 0) win_decode_level(loc, attw, dqm, LP, l, lv, pts[li], hmn, hmx, wmn, wmx);
+      if (dq >= 0) win_decode_level<LP>(loc, attw, dqm, l, lv, pts[li], hmn, hmx, wmn, wmx);
       hmn = __reduce_min_sync(0xffffffffu, hmn); hmx = __reduce_max_sync(0xffffffffu, hmx);
       wmn = __reduce_min_sync(0xffffffffu, wmn); wmx = __reduce_max_sync(0xffffffffu, wmx);
       if (lane == 0 && hmn <= hmx) {

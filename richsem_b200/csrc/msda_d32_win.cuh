@@ -143,7 +143,7 @@ struct WinCfg {
   static constexpr int OFF_ROWOFF = OFF_HIST + HIST_BYTES;
   static constexpr int OFF_SORTED = OFF_ROWOFF + ROWOFF_BYTES;
   static constexpr int INFLAG_BYTES = ((NLV * 4 * kWinTileQ + 127) / 128) * 128;
-  static constexpr int BWD_SMEM = OFF_SORTED + SORTED_BYTES + 192 + INFLAG_BYTES;
+  static constexpr int BWD_SMEM = OFF_SORTED + SORTED_BYTES + 192 + INFLAG_BYTES + kWinTileQ * 8;  // + softmax stats
   // deterministic mode: per-warp, per-cell sample counts (16-bit) that make the sort ranks scheduling-independent
   static constexpr int WCNT_BYTES = (kWinThreads / 32) * HIST_N * 2;
   static constexpr int BWD_DET_SMEM = ((BWD_SMEM + 15) / 16) * 16 + WCNT_BYTES;
@@ -254,14 +254,47 @@ __device__ __forceinline__ int win_record_code(const WinPoint& pt, const int bas
 }
 
 // Decodes the 4 points of level l of (query, head) qm and folds them into the thread's bounding box.
+// Softmax statistics of the L*P logits of one (query, head): max and sum of exp(x - max).  Every thread that
+// needs them reads the LP contiguous floats itself (the 4 level threads of a query sit in different warps;
+// re-reading 64 bytes from L2 is cheaper than a block barrier).
+template <int kLP>
+__device__ __forceinline__ float2 win_softmax_stats(const float* __restrict__ logits) {
+  float4 v[kLP / 4];
+#pragma unroll
+  for (int i = 0; i < kLP / 4; ++i) v[i] = ld_stream_f4(logits + 4 * i);
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kLP / 4; ++i) mx = fmaxf(fmaxf(mx, fmaxf(v[i].x, v[i].y)), fmaxf(v[i].z, v[i].w));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLP / 4; ++i) sum += __expf(v[i].x - mx) + __expf(v[i].y - mx) + __expf(v[i].z - mx) + __expf(v[i].w - mx);
+  return make_float2(mx, sum);
+}
+
+template <int kLP>
 __device__ __forceinline__ void win_decode_level(const float* __restrict__ loc, const float* __restrict__ attw,
-                                                 const size_t qm, const int LP, const int l, const MsdaLevels& lv,
-                                                 WinPoint (&pt)[4], int& hmn, int& hmx, int& wmn, int& wmx) {
+                                                 const size_t qm, const int l, const MsdaLevels& lv,
+                                                 WinPoint (&pt)[4], int& hmn, int& hmx, int& wmn, int& wmx,
+                                                 const MsdaFused fz = MsdaFused{nullptr, 0}, const size_t bq = 0,
+                                                 float2* stats = nullptr) {
+  constexpr int LP = kLP, num_levels = kLP / 4;
   const float* lp = loc + (qm * LP + l * 4) * 2;
-  const float4 xy01 = ld_stream_f4(lp), xy23 = ld_stream_f4(lp + 4);
-  const float4 aw = ld_stream_f4(attw + qm * LP + l * 4);
+  float4 xy01 = ld_stream_f4(lp), xy23 = ld_stream_f4(lp + 4);
+  float4 aw = ld_stream_f4(attw + qm * LP + l * 4);
   const int H = lv.H[l], W = lv.W[l];
   const bool fma = lv.coord_fma != 0;
+  if (fz.ref_dim) {  // fused prologue: raw offsets / logits -> locations / weights
+    const float2 st = win_softmax_stats<kLP>(attw + qm * LP);
+    if (stats) *stats = st;
+    aw = make_float4(__expf(aw.x - st.x) / st.y, __expf(aw.y - st.x) / st.y, __expf(aw.z - st.x) / st.y,
+                     __expf(aw.w - st.x) / st.y);
+    const float2 p0 = msda_fused_location(fz, bq, num_levels, l, 4, H, W, make_float2(xy01.x, xy01.y));
+    const float2 p1 = msda_fused_location(fz, bq, num_levels, l, 4, H, W, make_float2(xy01.z, xy01.w));
+    const float2 p2 = msda_fused_location(fz, bq, num_levels, l, 4, H, W, make_float2(xy23.x, xy23.y));
+    const float2 p3 = msda_fused_location(fz, bq, num_levels, l, 4, H, W, make_float2(xy23.z, xy23.w));
+    xy01 = make_float4(p0.x, p0.y, p1.x, p1.y);
+    xy23 = make_float4(p2.x, p2.y, p3.x, p3.y);
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float x = i == 0 ? xy01.x : i == 1 ? xy01.z : i == 2 ? xy23.x : xy23.z;
@@ -283,6 +316,7 @@ __device__ __forceinline__ void win_decode_level(const float* __restrict__ loc, 
 template <typename VT, int kL, int kWinPool, bool kBwd, bool kDetRank, class Sync>
 __device__ __forceinline__ void win_front_end(const int t, const Sync sync, unsigned short* wcnt, const VT* __restrict__ value_img, const float* __restrict__ loc,
                                               const float* __restrict__ attw, const int q, const size_t qm,
+                                              const MsdaFused fz, const size_t bq, float2* stats,
                                               const int qpf, const size_t qm_pf,
                                               const int m, const int M, const MsdaLevels& lv,
                                               unsigned char* pool, float4* rec, int* bb, int* rowoff, int* hist,
@@ -309,7 +343,7 @@ __device__ __forceinline__ void win_front_end(const int t, const Sync sync, unsi
 #pragma unroll
     for (int i = 0; i < 4; ++i) pts[li][i] = WinPoint{0, 0, 0.f, 0.f, 0.f, false};
     if (l < kL) {
-      if (q >= 0) win_decode_level(loc, attw, qm, Cfg::LP, l, lv, pts[li], hmn, hmx, wmn, wmx);
+      if (q >= 0) win_decode_level<Cfg::LP>(loc, attw, qm, l, lv, pts[li], hmn, hmx, wmn, wmx, fz, bq, li == 0 && slot == 0 ? stats : nullptr);
       if (qpf >= 0) {  // a later block's inputs: HBM -> L2 now, so that its decode sees L2 latency
         prefetch_l2(loc + (qm_pf * Cfg::LP + l * 4) * 2);
         prefetch_l2(attw + qm_pf * Cfg::LP + l * 4);
@@ -410,7 +444,7 @@ msda_fwd_d32_win_kernel(const VT* __restrict__ value, const float* __restrict__ 
     const size_t qm_pf = ((size_t)b * Lq + (qpf >= 0 ? qpf : 0)) * M + m;
     WinPoint pts[Cfg::NLV][4];
     int rank[Cfg::NLV][4];
-    win_front_end<VT, kL, kWinPool, false, false>(t, BlockSync{}, nullptr, value_img, loc, attw, q, qm, qpf, qm_pf, m, M, lv, pool, rec, bb, nullptr, nullptr, wa, pts, rank, tphase);
+    win_front_end<VT, kL, kWinPool, false, false>(t, BlockSync{}, nullptr, value_img, loc, attw, q, qm, MsdaFused{nullptr, 0}, 0, nullptr, qpf, qm_pf, m, M, lv, pool, rec, bb, nullptr, nullptr, wa, pts, rank, tphase);
   }
   WIN_T(1, tphase);  // allocation, staging issue, records
   cp_async_wait_all();
@@ -562,6 +596,7 @@ struct WinBwdSmem {
   float* lvf;              // [0,8) (float)W_l  [8,16) (float)H_l
   unsigned char* inflag;   // per (level slot, query): bit i = point i passed the range test
   unsigned short* wcnt;    // deterministic mode only: [warp][cell] counts, then exclusive bases over the warps
+  float2* stats;           // fused prologue only: softmax (max, sum) of every query of the tile
   __device__ __forceinline__ explicit WinBwdSmem(unsigned char* base)
       : pool(base),
         rec(reinterpret_cast<float4*>(base + Cfg::POOL_BYTES)),
@@ -573,6 +608,7 @@ struct WinBwdSmem {
         misc(reinterpret_cast<int*>(base + Cfg::OFF_SORTED + Cfg::SORTED_BYTES)),
         lvf(reinterpret_cast<float*>(base + Cfg::OFF_SORTED + Cfg::SORTED_BYTES) + 32),
         inflag(base + Cfg::OFF_SORTED + Cfg::SORTED_BYTES + 192),
+        stats(reinterpret_cast<float2*>(base + Cfg::OFF_SORTED + Cfg::SORTED_BYTES + 192 + Cfg::INFLAG_BYTES)),
         wcnt(reinterpret_cast<unsigned short*>(base + ((Cfg::BWD_SMEM + 15) / 16) * 16)) {}
 };
 
@@ -590,6 +626,9 @@ struct WinBwdArgs {
   // max|grad_out|, max|attn_weight| that fix their scale
   long long* gv64;
   const unsigned* maxbits;
+  // fused prologue (ref_dim != 0): loc / attw are the raw offsets / logits, grad_loc / grad_attw receive the
+  // gradients of the raw tensors
+  MsdaFused fz;
 };
 
 // Deterministic mode: scale (a power of two) that maps any sum of up to Lq*L*P products weight * grad_out,
@@ -632,7 +671,7 @@ __device__ __forceinline__ void quad_transpose4(float (&a)[4], const int q, cons
 // Producer half of a backward tile: decode, windows (staged with cp.async), records, counting sort,
 // grad_out rows.  `t` = thread index inside the kWinThreads-wide group that runs it, `sync` its barrier.
 // On return everything the consumer half needs is in the buffer set and visible to the group.
-template <typename VT, int kL, int kWinPool, bool kDet, class Sync>
+template <typename VT, int kL, int kWinPool, bool kDet, bool kFused, class Sync>
 __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, kWinPool>>& sm, const WinBwdArgs& ar,
                                                 const MsdaLevels& lv, const int tile, const int m, const int b,
                                                 const int t, const Sync sync) {
@@ -680,7 +719,9 @@ __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, 
   WinAlloc<kL> wa;
   WinPoint pts[Cfg::NLV][4];
   int rank[Cfg::NLV][4];
-  win_front_end<VT, kL, kWinPool, true, kDet>(t, sync, sm.wcnt, value_img, ar.loc, ar.attw, dq, dqm, qpf, qm_pf, m, M, lv, sm.pool, sm.rec,
+  win_front_end<VT, kL, kWinPool, true, kDet>(t, sync, sm.wcnt, value_img, ar.loc, ar.attw, dq, dqm,
+                                              kFused ? ar.fz : MsdaFused{nullptr, 0},
+                                              (size_t)b * Lq + (dq >= 0 ? dq : 0), kFused ? sm.stats + dql : nullptr, qpf, qm_pf, m, M, lv, sm.pool, sm.rec,
                                         sm.bb, sm.rowoff, sm.hist, wa, pts, rank, tphase);
 #pragma unroll
   for (int it = 0; it < GO_ITERS; ++it) {
@@ -758,7 +799,7 @@ __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, 
 }
 
 // Consumer half: sorted pass, direct pass, write-out (see the file header).
-template <typename VT, int kL, int kWinPool, bool kDet, class Sync>
+template <typename VT, int kL, int kWinPool, bool kDet, bool kFused, class Sync>
 __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, kWinPool>>& sm, const WinBwdArgs& ar,
                                                 const MsdaLevels& lv, const int tile, const int m, const int b,
                                                 const int t, const Sync sync) {
@@ -842,10 +883,10 @@ __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, 
       const int nb = min(4, i1 - ib);
       int nsid = 0;
       if (ib + 4 < i1) nsid = sorted[ib + 4];
-      float pgx[4], pgy[4], pga[4];
+      float pgx[4], pgy[4], pga[4], aws[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        pgx[u] = pgy[u] = pga[u] = 0.f;
+        pgx[u] = pgy[u] = pga[u] = aws[u] = 0.f;
         if (u < nb) {  // group-uniform
           const int sid = (int)(((u < 2 ? packed.x : packed.y) >> ((u & 1) * 16)) & 0xffffu);
           const int sq = sid / LP, l = (sid - sq * LP) >> 2;
@@ -885,6 +926,7 @@ __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, 
             cur0 = row0; cur1 = row1;
           }
           const float lh = r.y, lw = r.z, a = r.w;
+          if (kFused) aws[u] = a;
           const float hh = 1.f - lh, hw = 1.f - lw;
           const float2 go[SP] = {make_float2(ga4.x, ga4.y), make_float2(ga4.z, ga4.w), make_float2(gb4.x, gb4.y),
                                  make_float2(gb4.z, gb4.w)};
@@ -917,7 +959,8 @@ __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, 
       const float ga = group_reduce_scatter<4>(pga, sj, gmask);
       if (sj < nb) {  // lane sj owns sample ib + sj: park its gradients in the sample's record slot
         const int sid = (int)(((sj < 2 ? packed.x : packed.y) >> ((sj & 1) * 16)) & 0xffffu);
-        rec[rec_slot(sid)] = make_float4(gx, gy, ga, 0.f);
+        // .w keeps the sample's weight (the fused prologue's softmax backward needs it)
+        rec[rec_slot(sid)] = make_float4(gx, gy, ga, !kFused ? 0.f : sj == 0 ? aws[0] : sj == 1 ? aws[1] : sj == 2 ? aws[2] : aws[3]);
       }
     }
     if (cur0 >= 0) {
@@ -989,7 +1032,7 @@ __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, 
             gy += __shfl_xor_sync(0xffffffffu, gy, s);
           }
           __syncwarp();
-          if (j == 0) *slot = make_float4(gx, gy, ga, 0.f);
+          if (j == 0) *slot = make_float4(gx, gy, ga, a);
         }
       }
     }
@@ -1016,6 +1059,36 @@ __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, 
           r[i] = rec[dql * Cfg::REC_STRIDE + l * 4 + i];
           if (!(fl & (1 << i))) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // skipped sample: slot still holds its record
         }
+        if (kFused) {
+          // fused prologue: gradients of the raw offsets and logits.  softmax backward needs
+          // dot = sum_j a_j * dL/da_j over all L*P samples of (query, head): the other levels' dL/da sit in
+          // their record slots, the weights are recomputed from the logits and the saved (max, sum)
+          float dot = 0.f;
+          for (int sl = 0; sl < Cfg::NLV * 4; ++sl) {
+            const int l2 = (sl & 3) + 4 * (sl >> 2);
+            if (l2 < kL) {
+              const int f2 = sm.inflag[sl * kWinTileQ + dql];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 o = rec[dql * Cfg::REC_STRIDE + l2 * 4 + i];  // (gx, gy, dL/da, a) of a processed sample
+                if (f2 & (1 << i)) dot = fmaf(o.w, o.z, dot);
+              }
+            }
+          }
+          const float2 st = sm.stats[dql];
+          const float4 x = ld_stream_f4(ar.attw + dqm * LP + l * 4);
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+          const float* rp = ar.fz.ref + (((size_t)b * Lq + dq) * kL + l) * ar.fz.ref_dim;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            // a skipped sample has no result slot: its weight is recomputed (its dL/da is 0, not its dL/dlogit)
+            const float a = (fl & (1 << i)) ? rec[dql * Cfg::REC_STRIDE + l * 4 + i].w : __expf(xs[i] - st.x) / st.y;
+            // d loc / d offset, in autograd's operation order: g / W  |  ((g * 0.5) * wh) / P
+            const float gx = ar.fz.ref_dim == 2 ? r[i].x / (float)lv.W[l] : r[i].x * 0.5f * rp[2] / 4.f;
+            const float gy = ar.fz.ref_dim == 2 ? r[i].y / (float)lv.H[l] : r[i].y * 0.5f * rp[3] / 4.f;
+            r[i] = make_float4(gx, gy, a * (r[i].z - dot), 0.f);
+          }
+        }
         float* gl = ar.grad_loc + (dqm * LP + l * 4) * 2;
         st_stream_f4(gl, make_float4(r[0].x, r[0].y, r[1].x, r[1].y));
         st_stream_f4(gl + 4, make_float4(r[2].x, r[2].y, r[3].x, r[3].y));
@@ -1027,7 +1100,7 @@ __device__ __forceinline__ void win_bwd_consume(const WinBwdSmem<WinCfg<VT, kL, 
 
 // One block = one tile x one head: produce, then consume.  kDet: deterministic grad_value (canonical order
 // inside the block, order-independent fixed-point accumulation across blocks; see msda_capi.cu).
-template <typename VT, int kL, int kM, bool kDet>
+template <typename VT, int kL, int kM, bool kDet, bool kFused>
 __global__ void __launch_bounds__(kWinThreads, MSDA_WIN_BWD_MINBLOCKS)
 msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels lv) {
   constexpr int kWinPool = kWinPoolBwd;
@@ -1038,8 +1111,8 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
   WinBwdArgs a = ar;
   if (kM) a.M = kM;
   const int m = blockIdx.x % a.M, tile = blockIdx.x / a.M, b = blockIdx.y;
-  win_bwd_produce<VT, kL, kWinPool, kDet>(sm, a, lv, tile, m, b, (int)threadIdx.x, BlockSync{});
-  win_bwd_consume<VT, kL, kWinPool, kDet>(sm, a, lv, tile, m, b, (int)threadIdx.x, BlockSync{});
+  win_bwd_produce<VT, kL, kWinPool, kDet, kFused>(sm, a, lv, tile, m, b, (int)threadIdx.x, BlockSync{});
+  win_bwd_consume<VT, kL, kWinPool, kDet, kFused>(sm, a, lv, tile, m, b, (int)threadIdx.x, BlockSync{});
 }
 
 // Deterministic mode helpers: max|x| of a tensor as a float bit pattern (non-negative floats order like
@@ -1137,13 +1210,13 @@ msda_bwd_d32_ws_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels l
     if (role == 0) {
       if (use > 0) mbar_wait(bars + 2 + set, (use - 1) & 1);  // the consumer released the set
       if (t == 0) WIN_T(11, tph);  // producer waiting for a free buffer set
-      win_bwd_produce<VT, kL, kWinPool, false>(sm, a, lv, tile, m, b, t, GroupSync<1>{});
+      win_bwd_produce<VT, kL, kWinPool, false, false>(sm, a, lv, tile, m, b, t, GroupSync<1>{});
       if (t == 0) WIN_T(8, tph);   // produce
       if (t == 0) mbar_arrive(bars + set);
     } else {
       mbar_wait(bars + set, use & 1);
       if (t == 0) WIN_T(9, tph);   // consumer waiting for a full buffer set
-      win_bwd_consume<VT, kL, kWinPool, false>(sm, a, lv, tile, m, b, t, GroupSync<2>{});
+      win_bwd_consume<VT, kL, kWinPool, false, false>(sm, a, lv, tile, m, b, t, GroupSync<2>{});
       GroupSync<2>{}();  // every consumer thread is done with the set
       if (t == 0) WIN_T(10, tph);  // consume
 #ifdef MSDA_WIN_TIMING

@@ -24,6 +24,7 @@ struct Problem {
   const int32_t* order;
   int order_len;
   uint32_t flags;
+  MsdaFused fz;  // ref_dim 0: the reference op; 2 | 4: fused prologue (loc / attw are the raw Linear outputs)
 };
 
 // Few (query, head) pairs (decoder cross-attention): one warp per pair instead of one lane group.

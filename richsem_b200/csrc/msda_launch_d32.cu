@@ -15,7 +15,7 @@ int launch_fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const flo
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
   msda::msda_fwd_d32_kernel<VT, kL, 4, kM><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
       value, loc, attw, out, pb.order, pb.order_len, pb.lv, pb.d.spatial_size, pb.d.num_heads,
-      pb.d.num_query);
+      pb.d.num_query, pb.fz);
   return after_launch("msda_fwd_d32_kernel");
 }
 template <int kL, int kM>

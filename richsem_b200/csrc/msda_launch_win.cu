@@ -47,14 +47,15 @@ WinBwdArgs make_bwd_args(const Problem& pb, const VT* go, const VT* value, const
   a.order = pb.order; a.order_len = pb.order_len;
   a.S = pb.d.spatial_size; a.M = pb.d.num_heads; a.Lq = pb.d.num_query;
   a.gv64 = nullptr; a.maxbits = nullptr;
+  a.fz = pb.fz;
   return a;
 }
 
-template <typename VT, int kL, int kM, bool kDet>
+template <typename VT, int kL, int kM, bool kDet, bool kFused = false>
 int launch_bwd_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
                    const float* attw, float* gv, float* gl, float* ga, long long* gv64, const unsigned* maxbits) {
   using Cfg = WinCfg<VT, kL, kWinPoolBwd>;
-  constexpr auto kern = msda_bwd_d32_win_kernel<VT, kL, kM, kDet>;
+  constexpr auto kern = msda_bwd_d32_win_kernel<VT, kL, kM, kDet, kFused>;
   constexpr int kSmem = kDet ? Cfg::BWD_DET_SMEM : Cfg::BWD_SMEM;
   if (int rc = ensure_dynamic_smem<kern>(kSmem, "cudaFuncSetAttribute(msda_bwd_d32_win_kernel)")) return rc;
   const int tiles = (pb.order_len + kWinTileQ - 1) / kWinTileQ;
@@ -124,6 +125,13 @@ int bwd_d32_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value
   if (pb.flags & MSDA_FLAG_BWD_WS) {
     if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_bwd_ws<VT, 4, 8>(s, pb, go, value, loc, attw, gv, gl, ga);
 #define CALL(L) launch_bwd_ws<VT, L, 0>(s, pb, go, value, loc, attw, gv, gl, ga)
+    MSDA_SWITCH_L(pb.d.num_levels, CALL)
+#undef CALL
+  }
+  if (pb.fz.ref_dim) {  // fused prologue
+    if (pb.d.num_heads == 8 && pb.d.num_levels == 4)
+      return launch_bwd_win<VT, 4, 8, false, true>(s, pb, go, value, loc, attw, gv, gl, ga, nullptr, nullptr);
+#define CALL(L) launch_bwd_win<VT, L, 0, false, true>(s, pb, go, value, loc, attw, gv, gl, ga, nullptr, nullptr)
     MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL
   }

@@ -1,3 +1,3 @@
-from .msda_function import MSDeformAttnFunction
+from .msda_function import MSDeformAttnFunction, MSDeformAttnFusedFunction
 
-__all__ = ["MSDeformAttnFunction"]
+__all__ = ["MSDeformAttnFunction", "MSDeformAttnFusedFunction"]

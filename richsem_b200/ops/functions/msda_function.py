@@ -41,3 +41,40 @@ class MSDeformAttnFunction(Function):
         if g_value is not None and g_value.dtype != value.dtype:  # bf16 value: autograd wants the input's dtype
             g_value = g_value.to(value.dtype)
         return g_value, None, None, g_loc, g_weight, None
+
+
+class MSDeformAttnFusedFunction(Function):
+    """MSDeformAttn with the module's prologue fused into the kernels.
+
+        MSDeformAttnFusedFunction.apply(value, value_spatial_shapes, value_level_start_index,
+                                        reference_points, sampling_offsets, attention_logits, im2col_step)
+
+    takes the RAW outputs of the ``sampling_offsets`` / ``attention_weights`` Linear layers — (N, Lq, M, L, P, 2) and
+    (N, Lq, M, L*P) — plus ``reference_points`` (N, Lq, L, 2 | 4), and computes the softmax and the sampling locations
+    (/root/reference/models/richsem/ops/modules/ms_deform_attn.py:98-111) inside the kernels' decode step.  Gradients
+    are returned for value, sampling_offsets and attention_logits; reference_points gets none (RichSem computes them
+    without gradient: deformable_transformer.py:512-525 for the encoder, detached boxes in the decoder).
+    Only available where ``MultiScaleDeformableAttention.fused_prologue_supported`` says so.
+    """
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points, sampling_offsets,
+                attention_logits, im2col_step):
+        ctx.im2col_step = im2col_step
+        result = _ext.ms_deform_attn_forward_fused(value, value_spatial_shapes, value_level_start_index, reference_points,
+                                                   sampling_offsets, attention_logits, im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, reference_points, sampling_offsets,
+                              attention_logits)
+        return result
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, starts, ref, offsets, logits = ctx.saved_tensors
+        if ctx.needs_input_grad[3]:
+            raise RuntimeError("MSDeformAttnFusedFunction does not differentiate reference_points; use the unfused path")
+        g_value, g_off, g_logit = _ext.ms_deform_attn_backward_fused(
+            value, shapes, starts, ref, offsets, logits, grad_output.contiguous(), ctx.im2col_step)
+        if g_value.dtype != value.dtype:
+            g_value = g_value.to(value.dtype)
+        return g_value, None, None, None, g_off, g_logit, None

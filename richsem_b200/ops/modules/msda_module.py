@@ -16,7 +16,10 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ..functions import MSDeformAttnFunction
+import os
+
+from ... import MultiScaleDeformableAttention as _ext
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
 
 
 def _power_of_two(n) -> bool:
@@ -37,9 +40,13 @@ class MSDeformAttn(nn.Module):
         value_dtype: ``None`` keeps the reference behaviour (value in the input dtype);
             ``torch.bfloat16`` stores the projected value and the sampled output in bf16
             (fp32 accumulation, fp32 gradients).
+        fuse_prologue: compute the softmax and the sampling locations inside the kernels
+            (``MSDeformAttnFusedFunction``) wherever the library supports it — large encoder-style
+            calls — instead of five elementwise PyTorch kernels around the op.  Same results within
+            the op's tolerances; ``None`` reads ``MSDA_B200_FUSE_PROLOGUE`` (default off).
     """
 
-    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, value_dtype=None):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, value_dtype=None, fuse_prologue=None):
         super().__init__()
         if d_model % n_heads != 0:
             raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
@@ -49,6 +56,8 @@ class MSDeformAttn(nn.Module):
         self.im2col_step = 64  # kept for interface parity; the B200 kernels take the whole batch in one launch
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
         self.value_dtype = value_dtype
+        self.fuse_prologue = (os.environ.get("MSDA_B200_FUSE_PROLOGUE", "0") not in ("", "0")
+                              if fuse_prologue is None else bool(fuse_prologue))
 
         self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
         self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
@@ -96,6 +105,15 @@ class MSDeformAttn(nn.Module):
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(n, len_in, heads, self.d_model // heads)
         offsets = self.sampling_offsets(query).view(n, len_q, heads, levels, points, 2)
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
+        fused_value = value if self.value_dtype is None else value.to(self.value_dtype)
+        if (self.fuse_prologue and not reference_points.requires_grad and query.dtype == torch.float32
+                and _ext.fused_prologue_supported(fused_value, levels, len_q, points)):
+            logits = self.attention_weights(query).view(n, len_q, heads, levels * points)
+            sampled = MSDeformAttnFusedFunction.apply(fused_value, input_spatial_shapes, input_level_start_index,
+                                                      reference_points.contiguous(), offsets, logits, self.im2col_step)
+            return self.output_proj(sampled.to(query.dtype))
         weights = F.softmax(self.attention_weights(query).view(n, len_q, heads, levels * points), -1)
         weights = weights.view(n, len_q, heads, levels, points)
         if reference_points.shape[-1] == 2:

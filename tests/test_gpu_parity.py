@@ -424,3 +424,83 @@ def test_forward_backward_are_cuda_graph_capturable():
         assert torch.equal(out, want_out)
         assert rel_err(grads[0], want[0]) < 1e-5          # atomic order differs between runs
         assert rel_err(grads[1], want[1]) < 1e-6 and rel_err(grads[2], want[2]) < 1e-6
+
+
+@pytest.mark.parametrize("ref_dim,dtype", [(2, torch.float32), (4, torch.float32), (2, torch.bfloat16)])
+def test_fused_prologue_matches_the_unfused_path(ref_dim, dtype):
+    """softmax + sampling-location arithmetic inside the kernels.  The fused entry points, fed the raw
+    offsets / logits / reference points, must reproduce the reference op fed the module's own PyTorch expressions
+    (ms_deform_attn.py:98-111) — outputs and all gradients, through autograd for the raw tensors."""
+    from richsem_b200 import synthetic as syn
+    from richsem_b200.ops.functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
+
+    shapes = [(64, 84), (32, 42), (16, 21), (8, 11)]
+    dev = "cuda:0"
+    shp, starts, S = syn.level_tensors(shapes, dev)
+    g = torch.Generator(device=dev).manual_seed(17)
+    n, m, d, L, P = 2, 8, 32, 4, 4
+    value = torch.randn(n, S, m, d, generator=g, device=dev).to(dtype)
+    if ref_dim == 2:
+        ref = syn.encoder_reference_points(shapes, dev)[None, :, None, :].expand(n, S, L, 2).contiguous()
+        offsets = (syn.head_directions(m, dev)[None, None, :, None, None, :] * torch.arange(1, P + 1, device=dev).view(1, 1, 1, 1, P, 1)
+                   + 0.7 * torch.randn(n, S, m, L, P, 2, generator=g, device=dev)).contiguous()
+    else:
+        c = torch.rand(n, S, 1, 2, generator=g, device=dev)
+        wh = torch.rand(n, S, 1, 2, generator=g, device=dev) * 0.2 + 0.02
+        ref = torch.cat([c, wh], -1).expand(n, S, L, 4).contiguous()
+        offsets = (2.0 * torch.randn(n, S, m, L, P, 2, generator=g, device=dev)).contiguous()
+    logits = torch.randn(n, S, m, L * P, generator=g, device=dev)
+    grad_out = torch.randn(n, S, m * d, generator=g, device=dev).to(dtype)
+
+    def run(fused):
+        v = value.clone().requires_grad_(True)
+        off = offsets.clone().requires_grad_(True)
+        lg = logits.clone().requires_grad_(True)
+        if fused:
+            out = MSDeformAttnFusedFunction.apply(v, shp, starts, ref, off, lg, 64)
+        else:
+            w = torch.softmax(lg, -1).view(n, S, m, L, P)
+            if ref_dim == 2:
+                norm = torch.stack([shp[..., 1], shp[..., 0]], -1)
+                loc = ref[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+            else:
+                loc = ref[:, :, None, :, None, :2] + off / P * ref[:, :, None, :, None, 2:] * 0.5
+            out = MSDeformAttnFunction.apply(v, shp, starts, loc, w, 64)
+        out.backward(grad_out)
+        return out.detach(), v.grad, off.grad, lg.grad
+
+    a, b = run(True), run(False)
+    tol_f, tol_b = (FWD_TOL, BWD_TOL) if dtype == torch.float32 else (1e-2, 1e-2)
+    assert rel_err(a[0], b[0]) < tol_f
+    for x, y in zip(a[1:], b[1:]):
+        assert rel_err(x, y) < tol_b
+
+
+def test_module_with_fused_prologue_matches_the_default_module():
+    from richsem_b200 import synthetic as syn
+    from richsem_b200.ops.modules import MSDeformAttn
+
+    shapes = [(64, 84), (32, 42), (16, 21), (8, 11)]
+    dev = "cuda:0"
+    shp, starts, S = syn.level_tensors(shapes, dev)
+    torch.manual_seed(5)
+    plain = MSDeformAttn(256, 4, 8, 4).to(dev)
+    with torch.no_grad():  # away from the all-zero initialisation, so that every parameter gets a gradient
+        plain.sampling_offsets.weight.normal_(0, 0.02)
+        plain.attention_weights.weight.normal_(0, 0.05)
+    fused = MSDeformAttn(256, 4, 8, 4, fuse_prologue=True).to(dev)
+    fused.load_state_dict(plain.state_dict())
+    src = torch.randn(2, S, 256, device=dev)
+    ref = syn.encoder_reference_points(shapes, dev)[None, :, None, :].expand(2, S, 4, 2).contiguous()
+    mask = torch.zeros(2, S, dtype=torch.bool, device=dev)
+    mask[1, -500:] = True
+    outs = []
+    for mod in (plain, fused):
+        x = src.clone().requires_grad_(True)
+        y = mod(x, ref, x, shp, starts, mask)
+        y.square().mean().backward()
+        outs.append((y.detach(), x.grad, [p.grad for p in mod.parameters()]))
+    assert rel_err(outs[1][0], outs[0][0]) < 1e-5
+    assert rel_err(outs[1][1], outs[0][1]) < 1e-4
+    for gf, gp in zip(outs[1][2], outs[0][2]):
+        assert rel_err(gf, gp) < 1e-4
