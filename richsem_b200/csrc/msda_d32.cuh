@@ -212,9 +212,9 @@ msda_fwd_d32_kernel(const VT* __restrict__ value, const float* __restrict__ loc,
     __syncwarp();
 
     if (active) {
-      float acc[C];
+      float2 acc2[C / 2];  // channel pairs: the blends are packed FFMA2
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = 0.f;
+      for (int c = 0; c < C / 2; ++c) acc2[c] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int p = 0; p < LP; ++p) {
         const int l = p / kP;
@@ -229,28 +229,35 @@ msda_fwd_d32_kernel(const VT* __restrict__ value, const float* __restrict__ loc,
         if (bm & 1) {
           RT::load(p0, v);
           const float w = a_hh * hw;
+          const float2 w2 = make_float2(w, w);
 #pragma unroll
-          for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
+          for (int c = 0; c < C / 2; ++c) acc2[c] = ffma2(w2, make_float2(v[2 * c], v[2 * c + 1]), acc2[c]);
         }
         if (bm & 2) {
           RT::load(p0 + M32, v);
           const float w = a_hh * lw;
+          const float2 w2 = make_float2(w, w);
 #pragma unroll
-          for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
+          for (int c = 0; c < C / 2; ++c) acc2[c] = ffma2(w2, make_float2(v[2 * c], v[2 * c + 1]), acc2[c]);
         }
         if (bm & 4) {
           RT::load(p2, v);
           const float w = a_lh * hw;
+          const float2 w2 = make_float2(w, w);
 #pragma unroll
-          for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
+          for (int c = 0; c < C / 2; ++c) acc2[c] = ffma2(w2, make_float2(v[2 * c], v[2 * c + 1]), acc2[c]);
         }
         if (bm & 8) {
           RT::load(p2 + M32, v);
           const float w = a_lh * lw;
+          const float2 w2 = make_float2(w, w);
 #pragma unroll
-          for (int c = 0; c < C; ++c) acc[c] = fmaf(w, v[c], acc[c]);
+          for (int c = 0; c < C / 2; ++c) acc2[c] = ffma2(w2, make_float2(v[2 * c], v[2 * c + 1]), acc2[c]);
         }
       }
+      float acc[C];
+#pragma unroll
+      for (int c = 0; c < C / 2; ++c) { acc[2 * c] = acc2[c].x; acc[2 * c + 1] = acc2[c].y; }
       RT::store_stream(out + qm * 32 + j * C, acc);
     }
     __syncwarp();
