@@ -272,15 +272,31 @@ __device__ __forceinline__ float2 win_softmax_stats(const float* __restrict__ lo
 }
 
 template <int kLP>
+__device__ __forceinline__ void win_decode_loaded(float4 xy01, float4 xy23, float4 aw, const float* __restrict__ attw,
+                                                  const size_t qm, const int l, const MsdaLevels& lv,
+                                                  WinPoint (&pt)[4], int& hmn, int& hmx, int& wmn, int& wmx,
+                                                  const MsdaFused fz, const size_t bq, float2* stats);
+
+template <int kLP>
 __device__ __forceinline__ void win_decode_level(const float* __restrict__ loc, const float* __restrict__ attw,
                                                  const size_t qm, const int l, const MsdaLevels& lv,
                                                  WinPoint (&pt)[4], int& hmn, int& hmx, int& wmn, int& wmx,
                                                  const MsdaFused fz = MsdaFused{nullptr, 0}, const size_t bq = 0,
                                                  float2* stats = nullptr) {
+  const float* lp = loc + (qm * kLP + l * 4) * 2;
+  const float4 xy01 = ld_stream_f4(lp), xy23 = ld_stream_f4(lp + 4);
+  const float4 aw = ld_stream_f4(attw + qm * kLP + l * 4);
+  win_decode_loaded<kLP>(xy01, xy23, aw, attw, qm, l, lv, pt, hmn, hmx, wmn, wmx, fz, bq, stats);
+}
+
+// The same, with the level's raw 48 bytes already in registers (the front end issues those loads before its
+// first barrier).
+template <int kLP>
+__device__ __forceinline__ void win_decode_loaded(float4 xy01, float4 xy23, float4 aw, const float* __restrict__ attw,
+                                                  const size_t qm, const int l, const MsdaLevels& lv,
+                                                  WinPoint (&pt)[4], int& hmn, int& hmx, int& wmn, int& wmx,
+                                                  const MsdaFused fz, const size_t bq, float2* stats) {
   constexpr int LP = kLP, num_levels = kLP / 4;
-  const float* lp = loc + (qm * LP + l * 4) * 2;
-  float4 xy01 = ld_stream_f4(lp), xy23 = ld_stream_f4(lp + 4);
-  float4 aw = ld_stream_f4(attw + qm * LP + l * 4);
   const int H = lv.H[l], W = lv.W[l];
   const bool fma = lv.coord_fma != 0;
   if (fz.ref_dim) {  // fused prologue: raw offsets / logits -> locations / weights
@@ -325,6 +341,19 @@ __device__ __forceinline__ void win_front_end(const int t, const Sync sync, unsi
   using Cfg = WinCfg<VT, kL, kWinPool>;
   const int lane = t & 31;
   const int ql = t & (kWinTileQ - 1), slot = t / kWinTileQ;
+  // the decode's global loads go out first: their latency then covers the initialisation and the first barrier
+  float4 rxy01[Cfg::NLV], rxy23[Cfg::NLV], raw[Cfg::NLV];
+#pragma unroll
+  for (int li = 0; li < Cfg::NLV; ++li) {
+    const int l = slot + 4 * li;
+    rxy01[li] = rxy23[li] = raw[li] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l < kL && q >= 0) {
+      const float* lp = loc + (qm * Cfg::LP + l * 4) * 2;
+      rxy01[li] = ld_stream_f4(lp);
+      rxy23[li] = ld_stream_f4(lp + 4);
+      raw[li] = ld_stream_f4(attw + qm * Cfg::LP + l * 4);
+    }
+  }
   if (t < 32) bb[t] = (t & 8) ? INT_MIN : INT_MAX;  // [0,8) hmin [8,16) hmax [16,24) wmin [24,32) wmax
   if (t >= 32 && t < 32 + 2 * Cfg::ROWB / 16)
     reinterpret_cast<uint4*>(pool + kWinPool * Cfg::ROWB)[t - 32] = make_uint4(0u, 0u, 0u, 0u);
@@ -343,7 +372,9 @@ __device__ __forceinline__ void win_front_end(const int t, const Sync sync, unsi
 #pragma unroll
     for (int i = 0; i < 4; ++i) pts[li][i] = WinPoint{0, 0, 0.f, 0.f, 0.f, false};
     if (l < kL) {
-      if (q >= 0) win_decode_level<Cfg::LP>(loc, attw, qm, l, lv, pts[li], hmn, hmx, wmn, wmx, fz, bq, li == 0 && slot == 0 ? stats : nullptr);
+      if (q >= 0)
+        win_decode_loaded<Cfg::LP>(rxy01[li], rxy23[li], raw[li], attw, qm, l, lv, pts[li], hmn, hmx, wmn, wmx, fz, bq,
+                                   li == 0 && slot == 0 ? stats : nullptr);
       if (qpf >= 0) {  // a later block's inputs: HBM -> L2 now, so that its decode sees L2 latency
         prefetch_l2(loc + (qm_pf * Cfg::LP + l * 4) * 2);
         prefetch_l2(attw + qm_pf * Cfg::LP + l * 4);
