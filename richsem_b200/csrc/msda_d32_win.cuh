@@ -300,8 +300,7 @@ __device__ __forceinline__ void win_decode_loaded(float4 xy01, float4 xy23, floa
   const int H = lv.H[l], W = lv.W[l];
   const bool fma = lv.coord_fma != 0;
   if (fz.ref_dim) {  // fused prologue: raw offsets / logits -> locations / weights
-    const float2 st = win_softmax_stats<kLP>(attw + qm * LP);
-    if (stats) *stats = st;
+    const float2 st = stats ? *stats : win_softmax_stats<kLP>(attw + qm * LP);  // published by the front end, if any
     aw = make_float4(__expf(aw.x - st.x) / st.y, __expf(aw.y - st.x) / st.y, __expf(aw.z - st.x) / st.y,
                      __expf(aw.w - st.x) / st.y);
     const float2 p0 = msda_fused_location(fz, bq, num_levels, l, 4, H, W, make_float2(xy01.x, xy01.y));
@@ -354,6 +353,9 @@ __device__ __forceinline__ void win_front_end(const int t, const Sync sync, unsi
       raw[li] = ld_stream_f4(attw + qm * Cfg::LP + l * 4);
     }
   }
+  // fused prologue: the level-slot-0 thread of each query takes the softmax statistics of its L*P logits and
+  // publishes them through shared memory (the consume half needs them there anyway); the barrier below orders it
+  if (fz.ref_dim && slot == 0 && q >= 0 && stats != nullptr) *stats = win_softmax_stats<Cfg::LP>(attw + qm * Cfg::LP);
   if (t < 32) bb[t] = (t & 8) ? INT_MIN : INT_MAX;  // [0,8) hmin [8,16) hmax [16,24) wmin [24,32) wmax
   if (t >= 32 && t < 32 + 2 * Cfg::ROWB / 16)
     reinterpret_cast<uint4*>(pool + kWinPool * Cfg::ROWB)[t - 32] = make_uint4(0u, 0u, 0u, 0u);
@@ -373,8 +375,7 @@ __device__ __forceinline__ void win_front_end(const int t, const Sync sync, unsi
     for (int i = 0; i < 4; ++i) pts[li][i] = WinPoint{0, 0, 0.f, 0.f, 0.f, false};
     if (l < kL) {
       if (q >= 0)
-        win_decode_loaded<Cfg::LP>(rxy01[li], rxy23[li], raw[li], attw, qm, l, lv, pts[li], hmn, hmx, wmn, wmx, fz, bq,
-                                   li == 0 && slot == 0 ? stats : nullptr);
+        win_decode_loaded<Cfg::LP>(rxy01[li], rxy23[li], raw[li], attw, qm, l, lv, pts[li], hmn, hmx, wmn, wmx, fz, bq, stats);
       if (qpf >= 0) {  // a later block's inputs: HBM -> L2 now, so that its decode sees L2 latency
         prefetch_l2(loc + (qm_pf * Cfg::LP + l * 4) * 2);
         prefetch_l2(attw + qm_pf * Cfg::LP + l * 4);
