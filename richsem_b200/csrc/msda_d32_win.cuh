@@ -703,6 +703,9 @@ __device__ __forceinline__ void quad_transpose4(float (&a)[4], const int q, cons
 // Producer half of a backward tile: decode, windows (staged with cp.async), records, counting sort,
 // grad_out rows.  `t` = thread index inside the kWinThreads-wide group that runs it, `sync` its barrier.
 // On return everything the consumer half needs is in the buffer set and visible to the group.
+#ifndef MSDA_WIN_MATCH_RANK
+#define MSDA_WIN_MATCH_RANK 0  // 1: match-based (scheduling-independent) sort ranks in the atomic mode too
+#endif
 template <typename VT, int kL, int kWinPool, bool kDet, bool kFused, class Sync>
 __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, kWinPool>>& sm, const WinBwdArgs& ar,
                                                 const MsdaLevels& lv, const int tile, const int m, const int b,
@@ -710,6 +713,7 @@ __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, 
   using Cfg = WinCfg<VT, kL, kWinPool>;
   using RT = RowTraits<VT>;
   constexpr int LP = Cfg::LP, G = RT::G, C = RT::C;
+  constexpr bool kRank = kDet || (MSDA_WIN_MATCH_RANK != 0);
   const int M = ar.M, Lq = ar.Lq;
   const int warp = t >> 5, lane = t & 31;
   const VT* grad_out = static_cast<const VT*>(ar.grad_out);
@@ -751,7 +755,7 @@ __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, 
   WinAlloc<kL> wa;
   WinPoint pts[Cfg::NLV][4];
   int rank[Cfg::NLV][4];
-  win_front_end<VT, kL, kWinPool, true, kDet>(t, sync, sm.wcnt, value_img, ar.loc, ar.attw, dq, dqm,
+  win_front_end<VT, kL, kWinPool, true, kRank>(t, sync, sm.wcnt, value_img, ar.loc, ar.attw, dq, dqm,
                                               kFused ? ar.fz : MsdaFused{nullptr, 0},
                                               (size_t)b * Lq + (dq >= 0 ? dq : 0), kFused ? sm.stats + dql : nullptr, qpf, qm_pf, m, M, lv, sm.pool, sm.rec,
                                         sm.bb, sm.rowoff, sm.hist, wa, pts, rank, tphase);
@@ -776,7 +780,7 @@ __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, 
       if (l == t - 32) sm.misc[20 + l] = wa.base[l];
   }
   sync();  // hist complete, records visible
-  if (kDet) {
+  if (kRank) {
     // per cell: the warps' counts -> exclusive bases over the warps, their sum -> hist
     for (int c = t; c < Cfg::HIST_N; c += kWinThreads) {
       int run = 0;
@@ -821,7 +825,7 @@ __device__ __forceinline__ void win_bwd_produce(const WinBwdSmem<WinCfg<VT, kL, 
         if (rank[li][i] >= 0) {
           const int code = __float_as_int(sm.rec[dql * Cfg::REC_STRIDE + l * 4 + i].x);
           WIN_CHECK(sm.hist[code & 0xffff] + rank[li][i] >= 0 && sm.hist[code & 0xffff] + rank[li][i] < sm.misc[16]);
-          const int wbase = kDet ? (int)sm.wcnt[warp * Cfg::HIST_N + (code & 0xffff)] : 0;
+          const int wbase = kRank ? (int)sm.wcnt[warp * Cfg::HIST_N + (code & 0xffff)] : 0;
           sm.sorted[sm.hist[code & 0xffff] + wbase + rank[li][i]] = (unsigned short)(dql * LP + l * 4 + i);
         }
     }
