@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 1
+#define MSDA_ABI_VERSION 2
 #define MSDA_MAX_LEVELS 16
 
 /* status codes */
@@ -174,6 +174,39 @@ int msda_backward_fused_bf16(msda_stream_t stream, const uint16_t* grad_out, con
                              int num_heads, int channels, int num_levels, int num_query, int num_point,
                              float* grad_value, float* grad_sampling_offsets, float* grad_attn_logits,
                              const msda_opts* opts);
+
+/* ---- value preparation --------------------------------
+ * The module zeroes the padded tokens of the projected value (models/richsem/ops/modules/ms_deform_attn.py:95-96,
+ * `value.masked_fill(input_padding_mask[..., None], 0)`) before it is viewed as [batch, spatial_size, heads, channels]
+ * (:97).  `rows` = batch * spatial_size, `row_elems` = heads * channels (a multiple of 4); padding_mask is the
+ * module's bool mask, one byte per token, non-zero = padding.
+ *   msda_value_prepare_bf16    value_out[row,:] = mask[row] ? 0 : bf16(projected[row,:])   (mask may be NULL: cast only);
+ *                              feeds the bf16 kernels in one pass instead of masked_fill + cast
+ *   msda_zero_masked_rows_f32  in place: data[row,:] = 0 where mask[row]; only masked rows are written.  Serves the
+ *                              fp32 forward (on the projection's output) and the backward of both (on grad_value). */
+int msda_value_prepare_bf16(msda_stream_t stream, const float* projected, const uint8_t* padding_mask,
+                            long long rows, int row_elems, uint16_t* value_out);
+int msda_zero_masked_rows_f32(msda_stream_t stream, float* data, const uint8_t* padding_mask, long long rows,
+                              int row_elems);
+
+/* ---- two-stage proposals ------------------------------
+ * gen_encoder_output_proposals (models/richsem/utils.py:10-65) in one pass over the encoder memory:
+ *   memory            [batch, spatial_size, channels] fp32 (channels a multiple of 4)
+ *   padding_mask      [batch, spatial_size] bytes, non-zero = padding; NULL = no padding
+ *   spatial_shapes    [num_levels, 2] int64 DEVICE (H_l, W_l); levels lie back to back (utils.py:25,54); host mirror
+ *                     through msda_opts.spatial_shapes_host as for the op
+ *   wh_base           DEVICE float[2] = sigmoid(learnedwh) (utils.py:41), or NULL for the constant 0.05 (:43)
+ *   output_memory     [batch, spatial_size, channels]: memory, zero on padded or invalid tokens (:54-56)
+ *   output_proposals  [batch, spatial_size, 4]: logit of (cx, cy, w, h), +inf on padded or invalid tokens (:49-52)
+ *   valid_hw_workspace  DEVICE int32[batch * num_levels * 2], needed when padding_mask != NULL (valid H / W, :27-28)
+ * The backward routes grad_output_memory to the kept tokens (those whose proposal is finite). */
+int msda_encoder_proposals_f32(msda_stream_t stream, const float* memory, const uint8_t* padding_mask,
+                               const int64_t* spatial_shapes, const float* wh_base, int batch, int spatial_size,
+                               int channels, int num_levels, float* output_memory, float* output_proposals,
+                               int32_t* valid_hw_workspace, const msda_opts* opts);
+int msda_encoder_proposals_backward_f32(msda_stream_t stream, const float* grad_output_memory,
+                                        const float* output_proposals, int batch, int spatial_size, int channels,
+                                        float* grad_memory);
 
 /* ---- index contract probe --------------------------------------------------
  * Writes, for every sample (b,q,m,l,p), the four bilinear corner token indices

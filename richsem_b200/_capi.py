@@ -18,7 +18,7 @@ _LIB_PATH = Path(os.environ.get("MSDA_B200_LIB") or Path(__file__).resolve().par
 
 MSDA_OK = 0
 MSDA_ERR_UNSUPPORTED = 2
-MSDA_ABI_VERSION = 1
+MSDA_ABI_VERSION = 2
 FLAG_DETERMINISTIC = 0x1
 FLAG_GRAD_VALUE_PREZEROED = 0x2
 FLAG_FORCE_GENERIC = 0x4
@@ -77,6 +77,15 @@ def _load():
         f.argtypes, f.restype = fwd_fused, _i
         b = getattr(lib, f"msda_backward_fused_{sfx}")
         b.argtypes, b.restype = bwd_fused, _i
+    _ll = ctypes.c_longlong
+    lib.msda_value_prepare_bf16.argtypes = [_vp, _vp, _vp, _ll, _i, _vp]
+    lib.msda_value_prepare_bf16.restype = _i
+    lib.msda_zero_masked_rows_f32.argtypes = [_vp, _vp, _vp, _ll, _i]
+    lib.msda_zero_masked_rows_f32.restype = _i
+    lib.msda_encoder_proposals_f32.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, opts_p]
+    lib.msda_encoder_proposals_f32.restype = _i
+    lib.msda_encoder_proposals_backward_f32.argtypes = [_vp, _vp, _vp, _i, _i, _i, _vp]
+    lib.msda_encoder_proposals_backward_f32.restype = _i
     lib.msda_debug_corners_f32.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, opts_p]
     lib.msda_debug_corners_f32.restype = _i
     lib.msda_backward_workspace_bytes.argtypes = [_i] * 7

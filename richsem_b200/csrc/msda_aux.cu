@@ -1,0 +1,317 @@
+// msda_aux.cu — the elementwise passes either side of the sampling core:
+//
+//   * value preparation (models/richsem/ops/modules/ms_deform_attn.py:94-97): padding-mask zeroing of the
+//     projected value, fused with the bf16 cast the bf16 kernels want — one pass instead of masked_fill + to();
+//     for fp32 the rows are zeroed IN PLACE, so only the masked rows are written at all.
+//   * two-stage proposals (models/richsem/utils.py:10-65, gen_encoder_output_proposals): per-token anchor
+//     boxes in logit space + masked copy of the encoder memory — one pass over S tokens instead of ~25
+//     PyTorch kernels per call.
+//
+// All kernels are HBM-bound byte movers: one warp per token row, 16-byte streaming accesses, grid-stride
+// over a grid that is a multiple of the SM count.
+#include <cmath>
+#include <cstring>
+
+#include "msda_host.h"
+
+namespace {
+using msda::after_launch;
+using msda::check_cuda;
+using msda::fail;
+
+constexpr int kAuxThreads = 256;
+constexpr int kAuxBlocksPerSm = 8;
+constexpr int kSms = 148;
+
+inline int aux_grid(long long warps_needed) {
+  long long blocks = (warps_needed + kAuxThreads / 32 - 1) / (kAuxThreads / 32);
+  const long long cap = (long long)kSms * kAuxBlocksPerSm;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(float4* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void stg_stream(uint2* p, uint2 v) {
+  asm volatile("st.global.cs.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // round-to-nearest-even, as Tensor.to(bfloat16)
+  return r;
+}
+
+// ---- value preparation ------------------------------------------------------------------------------
+// out[row, :] = mask[row] ? 0 : bf16(in[row, :]).  One warp per row; row_elems % 4 == 0.  Masked rows are
+// not read.
+__global__ void __launch_bounds__(kAuxThreads)
+msda_value_prepare_bf16_kernel(const float* __restrict__ in, const uint8_t* __restrict__ mask,
+                               uint16_t* __restrict__ out, long long rows, int row_elems) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (kAuxThreads / 32) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (kAuxThreads / 32);
+  const int quads = row_elems >> 2;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const bool masked = mask != nullptr && mask[row] != 0;
+    const float4* src = reinterpret_cast<const float4*>(in + row * row_elems);
+    uint2* dst = reinterpret_cast<uint2*>(out + row * row_elems);
+    for (int i = lane; i < quads; i += 32) {
+      uint2 o = make_uint2(0u, 0u);
+      if (!masked) {
+        const float4 v = ldg_stream(src + i);
+        o.x = pack_bf16x2(v.x, v.y);
+        o.y = pack_bf16x2(v.z, v.w);
+      }
+      stg_stream(dst + i, o);
+    }
+  }
+}
+
+// data[row, :] = 0 where mask[row].  One warp per row; only masked rows are touched.
+__global__ void __launch_bounds__(kAuxThreads)
+msda_zero_masked_rows_kernel(float* __restrict__ data, const uint8_t* __restrict__ mask, long long rows,
+                             int row_elems) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (kAuxThreads / 32) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (kAuxThreads / 32);
+  const int quads = row_elems >> 2;
+  // a warp looks at 32 consecutive mask bytes at once and then zeroes the flagged rows one after another
+  for (long long base = warp0 * 32; base < rows; base += nwarps * 32) {
+    const long long mine = base + lane;
+    const bool flag = mine < rows && mask[mine] != 0;
+    unsigned todo = __ballot_sync(0xffffffffu, flag);
+    while (todo) {
+      const int r = __ffs(todo) - 1;
+      todo &= todo - 1;
+      float4* dst = reinterpret_cast<float4*>(data + (base + r) * row_elems);
+      for (int i = lane; i < quads; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// ---- two-stage proposals ----------------------------------------------------------------------------
+struct AuxLevels {
+  int H[MSDA_MAX_LEVELS];
+  int W[MSDA_MAX_LEVELS];
+  int start[MSDA_MAX_LEVELS];  // running sum of H*W (utils.py:25,54 `_cur`)
+  int num_levels;
+};
+
+// valid_hw[(b*L + l)*2 + {0,1}] = (#unmasked tokens in the first column, #unmasked tokens in the first row)
+// of level l of image b (utils.py:27-28).  One warp per (image, level).
+__global__ void msda_valid_hw_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ valid_hw,
+                                     const __grid_constant__ AuxLevels lv, int batch, int spatial_size) {
+  const int lane = threadIdx.x & 31;
+  const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (task >= batch * lv.num_levels) return;
+  const int b = task / lv.num_levels, l = task - b * lv.num_levels;
+  const int H = lv.H[l], W = lv.W[l];
+  const uint8_t* m = mask + (long long)b * spatial_size + lv.start[l];
+  int vh = 0, vw = 0;
+  for (int h = lane; h < H; h += 32) vh += m[(long long)h * W] == 0;
+  for (int w = lane; w < W; w += 32) vw += m[w] == 0;
+  for (int o = 16; o; o >>= 1) {
+    vh += __shfl_xor_sync(0xffffffffu, vh, o);
+    vw += __shfl_xor_sync(0xffffffffu, vw, o);
+  }
+  if (lane == 0) {
+    valid_hw[2 * task] = vh;
+    valid_hw[2 * task + 1] = vw;
+  }
+}
+
+// One warp per token: proposal (cx, cy, w, h) of utils.py:30-46 in logit space (:50-52), validity test (:49),
+// masked copy of the memory row (:54-56).  Same fp32 operations in the same order as the PyTorch expressions.
+__global__ void __launch_bounds__(kAuxThreads)
+msda_proposals_kernel(const float* __restrict__ memory, const uint8_t* __restrict__ mask,
+                      const int32_t* __restrict__ valid_hw, const float* __restrict__ wh_base,
+                      float* __restrict__ out_memory, float* __restrict__ out_proposals,
+                      const __grid_constant__ AuxLevels lv, int batch, int spatial_size, int channels) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (kAuxThreads / 32) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (kAuxThreads / 32);
+  const long long rows = (long long)batch * spatial_size;
+  const int quads = channels >> 2;
+  const float base_w = wh_base ? wh_base[0] : 0.05f;
+  const float base_h = wh_base ? wh_base[1] : 0.05f;
+  const float inf = __int_as_float(0x7f800000);
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const int b = (int)(row / spatial_size);
+    const int s = (int)(row - (long long)b * spatial_size);
+    int l = 0;
+#pragma unroll 1
+    for (int k = 1; k < lv.num_levels; ++k) l += s >= lv.start[k];
+    const int W = lv.W[l];
+    const int rel = s - lv.start[l];
+    const int y = rel / W, x = rel - y * W;
+    float vw = (float)W, vh = (float)lv.H[l];
+    bool masked = false;
+    if (mask != nullptr) {
+      masked = mask[row] != 0;
+      vh = (float)valid_hw[2 * (b * lv.num_levels + l)];
+      vw = (float)valid_hw[2 * (b * lv.num_levels + l) + 1];
+    }
+    const float scale_l = (float)(1 << l);  // 2.0 ** lvl (utils.py:41,43)
+    float p[4];
+    p[0] = __fdiv_rn((float)x + 0.5f, vw);
+    p[1] = __fdiv_rn((float)y + 0.5f, vh);
+    p[2] = __fmul_rn(base_w, scale_l);
+    p[3] = __fmul_rn(base_h, scale_l);
+    bool valid = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) valid = valid && (p[k] > 0.01f) && (p[k] < 0.99f);
+    const bool keep = valid && !masked;
+    if (lane == 0) {
+      float4 o;
+      o.x = keep ? logf(__fdiv_rn(p[0], __fsub_rn(1.f, p[0]))) : inf;
+      o.y = keep ? logf(__fdiv_rn(p[1], __fsub_rn(1.f, p[1]))) : inf;
+      o.z = keep ? logf(__fdiv_rn(p[2], __fsub_rn(1.f, p[2]))) : inf;
+      o.w = keep ? logf(__fdiv_rn(p[3], __fsub_rn(1.f, p[3]))) : inf;
+      stg_stream(reinterpret_cast<float4*>(out_proposals) + row, o);
+    }
+    const float4* src = reinterpret_cast<const float4*>(memory + row * channels);
+    float4* dst = reinterpret_cast<float4*>(out_memory + row * channels);
+    for (int i = lane; i < quads; i += 32)
+      stg_stream(dst + i, keep ? ldg_stream(src + i) : make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+
+// grad_memory[row, :] = kept(row) ? grad_output_memory[row, :] : 0, kept(row) <=> the row's proposal is finite.
+__global__ void __launch_bounds__(kAuxThreads)
+msda_proposals_backward_kernel(const float* __restrict__ grad_out, const float* __restrict__ proposals,
+                               float* __restrict__ grad_memory, long long rows, int channels) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (kAuxThreads / 32) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (kAuxThreads / 32);
+  const int quads = channels >> 2;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const bool keep = isfinite(proposals[4 * row]);
+    const float4* src = reinterpret_cast<const float4*>(grad_out + row * channels);
+    float4* dst = reinterpret_cast<float4*>(grad_memory + row * channels);
+    for (int i = lane; i < quads; i += 32)
+      stg_stream(dst + i, keep ? ldg_stream(src + i) : make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int resolve_aux_levels(cudaStream_t stream, const int64_t* shapes_dev, int num_levels, int spatial_size,
+                       const msda_opts* opts, AuxLevels* lv) {
+  if (num_levels < 1 || num_levels > MSDA_MAX_LEVELS)
+    return fail(MSDA_ERR_UNSUPPORTED, "num_levels=%d outside [1,%d]", num_levels, MSDA_MAX_LEVELS);
+  if (opts && opts->struct_size != sizeof(msda_opts))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_opts.struct_size=%u, library expects %zu", opts->struct_size,
+                sizeof(msda_opts));
+  int64_t shp[2 * MSDA_MAX_LEVELS];
+  if (opts && opts->spatial_shapes_host) {
+    memcpy(shp, opts->spatial_shapes_host, sizeof(int64_t) * 2 * num_levels);
+  } else {
+    if (!shapes_dev) return fail(MSDA_ERR_INVALID_ARGUMENT, "spatial_shapes is NULL");
+    cudaError_t e =
+        cudaMemcpyAsync(shp, shapes_dev, sizeof(int64_t) * 2 * num_levels, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return check_cuda(e, "copy of spatial_shapes to the host");
+  }
+  memset(lv, 0, sizeof(*lv));
+  lv->num_levels = num_levels;
+  long long cur = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    const int64_t H = shp[2 * l], W = shp[2 * l + 1];
+    if (H < 1 || W < 1 || H * W > INT32_MAX)
+      return fail(MSDA_ERR_INVALID_ARGUMENT, "level %d: bad shape (%lld,%lld)", l, (long long)H, (long long)W);
+    lv->H[l] = (int)H;
+    lv->W[l] = (int)W;
+    lv->start[l] = (int)cur;
+    cur += H * W;
+  }
+  if (cur != spatial_size)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "sum of H*W over the levels is %lld, spatial_size is %d", cur, spatial_size);
+  return MSDA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int msda_value_prepare_bf16(msda_stream_t stream, const float* projected, const uint8_t* padding_mask,
+                            long long rows, int row_elems, uint16_t* value_out) {
+  if (rows < 0 || row_elems < 4 || (row_elems & 3))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "rows=%lld row_elems=%d (row_elems must be a positive multiple of 4)", rows,
+                row_elems);
+  if (rows == 0) return MSDA_OK;
+  if (!projected || !value_out) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  if (!aligned16(projected) || (reinterpret_cast<uintptr_t>(value_out) & 7u))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "projected must be 16-byte aligned and value_out 8-byte aligned");
+  msda_value_prepare_bf16_kernel<<<aux_grid(rows), kAuxThreads, 0, (cudaStream_t)stream>>>(
+      projected, padding_mask, value_out, rows, row_elems);
+  return after_launch("msda_value_prepare_bf16_kernel");
+}
+
+int msda_zero_masked_rows_f32(msda_stream_t stream, float* data, const uint8_t* padding_mask, long long rows,
+                              int row_elems) {
+  if (rows < 0 || row_elems < 4 || (row_elems & 3))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "rows=%lld row_elems=%d (row_elems must be a positive multiple of 4)", rows,
+                row_elems);
+  if (rows == 0) return MSDA_OK;
+  if (!data || !padding_mask) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  if (!aligned16(data)) return fail(MSDA_ERR_INVALID_ARGUMENT, "data must be 16-byte aligned");
+  msda_zero_masked_rows_kernel<<<aux_grid((rows + 31) / 32), kAuxThreads, 0, (cudaStream_t)stream>>>(
+      data, padding_mask, rows, row_elems);
+  return after_launch("msda_zero_masked_rows_kernel");
+}
+
+int msda_encoder_proposals_f32(msda_stream_t stream, const float* memory, const uint8_t* padding_mask,
+                               const int64_t* spatial_shapes, const float* wh_base, int batch, int spatial_size,
+                               int channels, int num_levels, float* output_memory, float* output_proposals,
+                               int32_t* valid_hw_workspace, const msda_opts* opts) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (batch < 0 || spatial_size < 1 || channels < 4 || (channels & 3))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "bad dimensions: batch=%d spatial_size=%d channels=%d (multiple of 4)",
+                batch, spatial_size, channels);
+  AuxLevels lv;
+  const int rc = resolve_aux_levels(s, spatial_shapes, num_levels, spatial_size, opts, &lv);
+  if (rc != MSDA_OK) return rc;
+  if (batch == 0) return MSDA_OK;
+  if (!memory || !output_memory || !output_proposals) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  if (!aligned16(memory) || !aligned16(output_memory) || !aligned16(output_proposals))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "memory / output_memory / output_proposals must be 16-byte aligned");
+  if (padding_mask) {
+    if (!valid_hw_workspace)
+      return fail(MSDA_ERR_WORKSPACE, "a padding mask needs valid_hw_workspace (batch * num_levels * 2 int32)");
+    const int tasks = batch * num_levels;
+    msda_valid_hw_kernel<<<(tasks + 3) / 4, 128, 0, s>>>(padding_mask, valid_hw_workspace, lv, batch, spatial_size);
+    const int rc2 = after_launch("msda_valid_hw_kernel");
+    if (rc2 != MSDA_OK) return rc2;
+  }
+  msda_proposals_kernel<<<aux_grid((long long)batch * spatial_size), kAuxThreads, 0, s>>>(
+      memory, padding_mask, valid_hw_workspace, wh_base, output_memory, output_proposals, lv, batch, spatial_size,
+      channels);
+  return after_launch("msda_proposals_kernel");
+}
+
+int msda_encoder_proposals_backward_f32(msda_stream_t stream, const float* grad_output_memory,
+                                        const float* output_proposals, int batch, int spatial_size, int channels,
+                                        float* grad_memory) {
+  if (batch < 0 || spatial_size < 1 || channels < 4 || (channels & 3))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "bad dimensions: batch=%d spatial_size=%d channels=%d (multiple of 4)",
+                batch, spatial_size, channels);
+  if (batch == 0) return MSDA_OK;
+  if (!grad_output_memory || !output_proposals || !grad_memory)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  if (!aligned16(grad_output_memory) || !aligned16(grad_memory) || !aligned16(output_proposals))
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "tensors must be 16-byte aligned");
+  const long long rows = (long long)batch * spatial_size;
+  msda_proposals_backward_kernel<<<aux_grid(rows), kAuxThreads, 0, (cudaStream_t)stream>>>(
+      grad_output_memory, output_proposals, grad_memory, rows, channels);
+  return after_launch("msda_proposals_backward_kernel");
+}
+
+}  // extern "C"

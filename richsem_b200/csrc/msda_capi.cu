@@ -383,7 +383,9 @@ int msda_has_fast_path(int dtype_bytes, int channels, int num_levels, int num_po
 
 int msda_abi_version(void) { return MSDA_ABI_VERSION; }
 
-const char* msda_build_info(void) { return "msda_b200 abi " "1" " sm_100a " __DATE__ " " __TIME__; }
+#define MSDA_STR_(x) #x
+#define MSDA_STR(x) MSDA_STR_(x)
+const char* msda_build_info(void) { return "msda_b200 abi " MSDA_STR(MSDA_ABI_VERSION) " sm_100a " __DATE__ " " __TIME__; }
 
 const char* msda_last_error(void) { return g_err; }
 

@@ -1,3 +1,4 @@
+from .aux_functions import gen_encoder_output_proposals, prepare_value
 from .msda_function import MSDeformAttnFunction, MSDeformAttnFusedFunction
 
-__all__ = ["MSDeformAttnFunction", "MSDeformAttnFusedFunction"]
+__all__ = ["MSDeformAttnFunction", "MSDeformAttnFusedFunction", "prepare_value", "gen_encoder_output_proposals"]

@@ -19,7 +19,7 @@ from torch import nn
 import os
 
 from ... import MultiScaleDeformableAttention as _ext
-from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, prepare_value
 
 
 def _power_of_two(n) -> bool:
@@ -100,14 +100,14 @@ class MSDeformAttn(nn.Module):
         assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == len_in
 
         heads, levels, points = self.n_heads, self.n_levels, self.n_points
-        value = self.value_proj(input_flatten)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        # ms_deform_attn.py:94-97: projection, padded tokens zeroed, (N, S, M, D) view — the zeroing (in place for
+        # fp32) and the optional bf16 cast are one pass of csrc/msda_aux.cu
+        value = prepare_value(self.value_proj(input_flatten), input_padding_mask, self.value_dtype)
         value = value.view(n, len_in, heads, self.d_model // heads)
         offsets = self.sampling_offsets(query).view(n, len_q, heads, levels, points, 2)
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
-        fused_value = value if self.value_dtype is None else value.to(self.value_dtype)
+        fused_value = value
         if (self.fuse_prologue and not reference_points.requires_grad and query.dtype == torch.float32
                 and _ext.fused_prologue_supported(fused_value, levels, len_q, points)):
             logits = self.attention_weights(query).view(n, len_q, heads, levels * points)
@@ -127,8 +127,8 @@ class MSDeformAttn(nn.Module):
         else:
             raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
 
-        if self.value_dtype is not None and value.dtype != self.value_dtype:
-            sampled = MSDeformAttnFunction.apply(value.to(self.value_dtype), input_spatial_shapes,
+        if self.value_dtype is not None and value.dtype != query.dtype:
+            sampled = MSDeformAttnFunction.apply(value, input_spatial_shapes,
                                                  input_level_start_index, locations.float(), weights.float(),
                                                  self.im2col_step).to(query.dtype)
         else:

@@ -1,0 +1,115 @@
+"""Times the elementwise passes of csrc/msda_aux.cu against their PyTorch equivalents at the DINO shape
+ and prints one JSON line per pass: algorithmic bytes, time, GB/s, fraction of the
+measured HBM peak.  Inputs are rotated over enough distinct buffers to exceed L2.
+
+    python scratch/aux_bench.py [--batch 2] [--iters 50]
+"""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from richsem_b200 import synthetic as syn  # noqa: E402
+from richsem_b200.ops.functions import gen_encoder_output_proposals  # noqa: E402
+from richsem_b200.ops.functions.aux_functions import cast_value_bf16, zero_masked_rows_  # noqa: E402
+
+
+def peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    return float(json.loads(p.read_text())["hbm_gbs"]) if p.exists() else 6650.0
+
+
+def rect(shapes, frac):
+    parts = []
+    for h, w in shapes:
+        m = torch.ones(h, w, dtype=torch.bool)
+        m[: max(1, round(h * frac[0])), : max(1, round(w * frac[1]))] = False
+        parts.append(m.reshape(-1))
+    return torch.cat(parts)
+
+
+def timeit(fns, iters):
+    """fns: list of closures over distinct buffers (rotated).  Returns ms per call (CUDA events)."""
+    for f in fns:
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fns[i % len(fns)]()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--iters", type=int, default=60)
+    ap.add_argument("--sets", type=int, default=6)
+    a = ap.parse_args()
+    dev = "cuda:0"
+    shapes = syn.level_shapes(800, 1333)
+    S = sum(h * w for h, w in shapes)
+    n, c = a.batch, 256
+    shp = torch.as_tensor(shapes, dtype=torch.long, device=dev)
+    mask = torch.stack([rect(shapes, (1.0, 1.0) if i % 2 == 0 else (0.8, 0.7)) for i in range(n)]).to(dev)
+    masked_rows = int(mask.sum())
+    xs = [torch.randn(n, S, c, device=dev) for _ in range(a.sets)]
+    pk = peak()
+    rows = n * S
+
+    def report(name, ms, alg_bytes, torch_ms, note):
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        print(json.dumps({"pass": name, "batch": n, "S": S, "C": c, "ms": ms, "algorithmic_bytes": alg_bytes,
+                          "GBps": gbs, "frac_of_hbm_peak": gbs / pk, "peak_GBps": pk, "torch_ms": torch_ms,
+                          "speedup_vs_torch": torch_ms / ms, "note": note}))
+
+    # 8f-2, bf16: read fp32 (unmasked rows) + mask, write bf16
+    alg = (rows - masked_rows) * c * 4 + rows + rows * c * 2
+    ms = timeit([lambda x=x: cast_value_bf16(x, mask) for x in xs], a.iters)
+    tms = timeit([lambda x=x: x.masked_fill(mask[..., None], 0.0).to(torch.bfloat16) for x in xs], a.iters)
+    report("value_prepare_bf16", ms, alg, tms, "vs masked_fill + to(bf16)")
+    # 8f-2, fp32 in place: read mask, write masked rows
+    alg = rows + masked_rows * c * 4
+    ms = timeit([lambda x=x: zero_masked_rows_(x, mask) for x in xs], a.iters)
+    tms = timeit([lambda x=x: x.masked_fill(mask[..., None], 0.0) for x in xs], a.iters)
+    report("zero_masked_rows_f32", ms, alg, tms, "vs out-of-place masked_fill")
+    # 8f-4: read memory (kept rows) + mask, write memory + proposals
+    sys.path.insert(0, str(ROOT))
+    from oracle.aux_oracle import encoder_proposals  # checker only: which rows are kept
+
+    keep = int(torch.isfinite(encoder_proposals(torch.zeros(n, S, 4), mask.cpu(), shapes)[1][..., 0]).sum())
+    alg = keep * c * 4 + rows + rows * c * 4 + rows * 16
+    ms = timeit([lambda x=x: gen_encoder_output_proposals(x, mask, shp) for x in xs], a.iters)
+
+    def torch_proposals(memory):
+        # the reference's expression sequence (utils.py:10-65), restated for timing only
+        props, cur = [], 0
+        for lvl, (h, w) in enumerate(shapes):
+            m = mask[:, cur:cur + h * w].view(n, h, w, 1)
+            vh, vw = torch.sum(~m[:, :, 0, 0], 1), torch.sum(~m[:, 0, :, 0], 1)
+            gy, gx = torch.meshgrid(torch.linspace(0, h - 1, h, dtype=torch.float32, device=dev),
+                                    torch.linspace(0, w - 1, w, dtype=torch.float32, device=dev), indexing="ij")
+            grid = torch.cat([gx.unsqueeze(-1), gy.unsqueeze(-1)], -1)
+            scale = torch.cat([vw.unsqueeze(-1), vh.unsqueeze(-1)], 1).view(n, 1, 1, 2)
+            grid = (grid.unsqueeze(0).expand(n, -1, -1, -1) + 0.5) / scale
+            wh = torch.ones_like(grid) * 0.05 * (2.0 ** lvl)
+            props.append(torch.cat((grid, wh), -1).view(n, -1, 4))
+            cur += h * w
+        p = torch.cat(props, 1)
+        valid = ((p > 0.01) & (p < 0.99)).all(-1, keepdim=True)
+        p = torch.log(p / (1 - p)).masked_fill(mask.unsqueeze(-1), float("inf")).masked_fill(~valid, float("inf"))
+        om = memory.masked_fill(mask.unsqueeze(-1), 0.0).masked_fill(~valid, 0.0)
+        return om, p
+
+    tms = timeit([lambda x=x: torch_proposals(x) for x in xs], a.iters)
+    report("encoder_proposals_f32", ms, alg, tms, "vs the reference's PyTorch expression sequence (utils.py:10-65)")
+
+
+if __name__ == "__main__":
+    main()
