@@ -48,19 +48,28 @@ WORKLOADS = {
     "encoder1_hr2000": ((1600, 2000), 1, 2, "E", None, "f32"),
     # config 4: whole encoder-layer train step (MSDeformAttn + Linear projections + FFN), DDP all-reduce
     "encoder_layer_ddp": ((800, 1333), 1, 2, "layer", None, "f32"),
+    # the whole 6-layer deformable encoder (MSDeformAttn + Linears + LayerNorm + FFN), forward + backward,
+    # captured in one CUDA graph; --eager replays it launch by launch instead
+    "encoder_stack6": ((800, 1333), 6, 2, "stack", None, "f32"),
 }
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="encoder6", choices=sorted(WORKLOADS))
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--lib-flags", type=lambda x: int(x, 0), default=0,
                     help="extra MSDA_FLAG_* bits for forward and backward (kernel-selection experiments)")
+    ap.add_argument("--eager", action="store_true", help="encoder_stack6: no CUDA graph")
+    ap.add_argument("--fuse-prologue", action="store_true", help="encoder_stack6: fused softmax + "
+                    "sampling-location prologue (SURVEY 8f-1)")
+    ap.add_argument("--tf32", action="store_true", help="encoder_stack6: let the PyTorch Linear layers use TF32 tensor "
+                    "cores (torch.backends.cuda.matmul.allow_tf32); the default is the reference's strict fp32")
+    ap.add_argument("--padding", action="store_true", help="encoder_stack6: image 1 of each pair is padded (mask path)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=8)
@@ -231,6 +240,8 @@ def run_b200(args):
     hw, layers, bs, kind, lq, vdt = WORKLOADS[args.workload]
     if kind == "layer":
         return run_encoder_layer_ddp(args, torch, dist, rank, world, dev)
+    if kind == "stack":
+        return run_encoder_stack(args, torch, dist, rank, world, dev)
     shapes = syn.level_shapes(*hw)
     tdt = torch.bfloat16 if vdt == "bf16" else torch.float32
     sets = [syn.make_inputs(kind, bs, shapes, dev, seed=rank_seed(1234, rank, i), lq=lq, dtype=tdt) for i in range(layers)]
@@ -404,6 +415,101 @@ def run_encoder_layer_ddp(args, torch, dist, rank, world, dev):
                        "step": "encoder layer fwd + bwd (MSDeformAttn on libmsda_b200, Linears/LayerNorm in PyTorch), "
                                "no optimizer"},
             "gpu_launches": int(launches), "clocks": clocks, "lib": _capi.build_info()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_encoder_stack(args, torch, dist, rank, world, dev):
+    """per rank the 6-layer deformable encoder (deformable_transformer.py:470-618, 825-881; d_ffn 2048,
+    relu, dropout 0) on its own bs=2 shard, forward + backward of loss = out.square().mean(), captured once in a CUDA
+    graph and replayed (or launched eagerly with --eager).  No optimizer, no collective (single-rank glue measurement;
+    under torchrun every rank runs its own replica and the slowest one counts)."""
+    from richsem_b200 import _capi, synthetic as syn
+    from richsem_b200.encoder_layer import DeformableEncoder, GraphedTrainStep
+
+    hw, layers, bs, _, _, _ = WORKLOADS[args.workload]
+    if args.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+    shapes = syn.level_shapes(*hw)
+    shp, st, S = syn.level_tensors(shapes, dev)
+    torch.manual_seed(1234)
+    model = DeformableEncoder(layers, fuse_prologue=args.fuse_prologue).to(dev)
+    with torch.no_grad():  # leave the degenerate init so that every gradient path does real work
+        for layer in model.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    src = torch.randn(bs, S, 256, generator=gen, device=dev)
+    pos = torch.randn(bs, S, 256, generator=gen, device=dev)
+    valid = torch.ones(bs, len(shapes), 2, device=dev)
+    mask = None
+    if args.padding:
+        rows = []
+        for i in range(bs):
+            fh, fw = (1.0, 1.0) if i % 2 == 0 else (0.8, 0.7)
+            parts = []
+            for h, w in shapes:
+                m = torch.ones(h, w, dtype=torch.bool)
+                m[: max(1, round(h * fh)), : max(1, round(w * fw))] = False
+                parts.append(m.reshape(-1))
+            rows.append(torch.cat(parts))
+            valid[i, :, 0], valid[i, :, 1] = fw, fh
+        mask = torch.stack(rows).to(dev)
+    loss_fn = lambda out: out.square().mean()
+    call_args = (src, pos, shp, st, valid, mask)
+
+    def eager_step():
+        for p in model.parameters():
+            p.grad = None
+        loss_fn(model(*call_args)).backward()
+
+    l0 = _capi.launch_count()
+    eager_step()
+    launches_per_step = _capi.launch_count() - l0
+    if args.eager:
+        step = eager_step
+    else:
+        graphed = GraphedTrainStep(model, loss_fn, call_args)
+        step = lambda: graphed.graph.replay()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    l0 = _capi.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = _capi.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / args.steps
+    if rank == 0:
+        n_params = sum(p.numel() for p in model.parameters())
+        print(json.dumps({
+            "metric": METRIC, "value": world * layers * bs * S / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "image": f"{hw[0]}x{hw[1]}", "S": S, "batch_per_gpu": bs,
+                       "layers_per_step": layers, "params": n_params, "mode": "eager" if args.eager else "cuda graph",
+                       "fuse_prologue": bool(args.fuse_prologue), "padding_mask": bool(args.padding),
+                       "linear_precision": "tf32" if args.tf32 else "fp32 (reference default)",
+                       "parallelism": f"replicas x{world}, no collective",
+                       "step": "6-layer deformable encoder fwd + bwd (MSDeformAttn + elementwise neighbours on "
+                               "libmsda_b200, Linears/LayerNorm/FFN in PyTorch), no optimizer"},
+            # a replayed graph launches the library's kernels without passing through its host entry points:
+            # the count below is what the capture recorded times the replays
+            "gpu_launches": int(launches) if args.eager else int(launches_per_step * args.steps),
+            "clocks": clocks, "lib": _capi.build_info()}))
     if world > 1:
         dist.destroy_process_group()
 

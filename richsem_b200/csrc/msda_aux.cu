@@ -60,18 +60,30 @@ msda_value_prepare_bf16_kernel(const float* __restrict__ in, const uint8_t* __re
   const long long warp0 = (long long)blockIdx.x * (kAuxThreads / 32) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (kAuxThreads / 32);
   const int quads = row_elems >> 2;
-  for (long long row = warp0; row < rows; row += nwarps) {
-    const bool masked = mask != nullptr && mask[row] != 0;
-    const float4* src = reinterpret_cast<const float4*>(in + row * row_elems);
-    uint2* dst = reinterpret_cast<uint2*>(out + row * row_elems);
-    for (int i = lane; i < quads; i += 32) {
-      uint2 o = make_uint2(0u, 0u);
-      if (!masked) {
-        const float4 v = ldg_stream(src + i);
-        o.x = pack_bf16x2(v.x, v.y);
-        o.y = pack_bf16x2(v.z, v.w);
+  // two rows per warp and iteration, every load issued before the first store: 4 x 16 bytes in flight per lane at
+  // 256 channels
+  for (long long row = warp0; row < rows; row += 2 * nwarps) {
+    const long long row2 = row + nwarps;
+    const bool has2 = row2 < rows;
+    const bool live1 = !(mask != nullptr && mask[row] != 0);
+    const bool live2 = has2 && !(mask != nullptr && mask[row2] != 0);
+    const float4* src1 = reinterpret_cast<const float4*>(in + row * row_elems);
+    const float4* src2 = reinterpret_cast<const float4*>(in + row2 * row_elems);
+    uint2* dst1 = reinterpret_cast<uint2*>(out + row * row_elems);
+    uint2* dst2 = reinterpret_cast<uint2*>(out + row2 * row_elems);
+    for (int i = lane; i < quads; i += 64) {
+      const bool b = i + 32 < quads;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v1a = live1 ? ldg_stream(src1 + i) : z;
+      const float4 v1b = (live1 && b) ? ldg_stream(src1 + i + 32) : z;
+      const float4 v2a = live2 ? ldg_stream(src2 + i) : z;
+      const float4 v2b = (live2 && b) ? ldg_stream(src2 + i + 32) : z;
+      stg_stream(dst1 + i, make_uint2(pack_bf16x2(v1a.x, v1a.y), pack_bf16x2(v1a.z, v1a.w)));
+      if (b) stg_stream(dst1 + i + 32, make_uint2(pack_bf16x2(v1b.x, v1b.y), pack_bf16x2(v1b.z, v1b.w)));
+      if (has2) {
+        stg_stream(dst2 + i, make_uint2(pack_bf16x2(v2a.x, v2a.y), pack_bf16x2(v2a.z, v2a.w)));
+        if (b) stg_stream(dst2 + i + 32, make_uint2(pack_bf16x2(v2b.x, v2b.y), pack_bf16x2(v2b.z, v2b.w)));
       }
-      stg_stream(dst + i, o);
     }
   }
 }
@@ -95,6 +107,20 @@ msda_zero_masked_rows_kernel(float* __restrict__ data, const uint8_t* __restrict
       float4* dst = reinterpret_cast<float4*>(data + (base + r) * row_elems);
       for (int i = lane; i < quads; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+}
+
+// dst[row] = keep ? src[row] : 0 for one row of `quads` float4; the loads of a 64-quad chunk are issued before its stores.
+__device__ __forceinline__ void copy_row_or_zero(const float4* __restrict__ src, float4* __restrict__ dst, int quads,
+                                                 int lane, bool keep) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = lane; i < quads; i += 128) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (keep && i + 32 * u < quads) ? ldg_stream(src + i + 32 * u) : z;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + 32 * u < quads) stg_stream(dst + i + 32 * u, v[u]);
   }
 }
 
@@ -178,10 +204,8 @@ msda_proposals_kernel(const float* __restrict__ memory, const uint8_t* __restric
       o.w = keep ? logf(__fdiv_rn(p[3], __fsub_rn(1.f, p[3]))) : inf;
       stg_stream(reinterpret_cast<float4*>(out_proposals) + row, o);
     }
-    const float4* src = reinterpret_cast<const float4*>(memory + row * channels);
-    float4* dst = reinterpret_cast<float4*>(out_memory + row * channels);
-    for (int i = lane; i < quads; i += 32)
-      stg_stream(dst + i, keep ? ldg_stream(src + i) : make_float4(0.f, 0.f, 0.f, 0.f));
+    copy_row_or_zero(reinterpret_cast<const float4*>(memory + row * channels),
+                     reinterpret_cast<float4*>(out_memory + row * channels), quads, lane, keep);
   }
 }
 
@@ -195,10 +219,8 @@ msda_proposals_backward_kernel(const float* __restrict__ grad_out, const float* 
   const int quads = channels >> 2;
   for (long long row = warp0; row < rows; row += nwarps) {
     const bool keep = isfinite(proposals[4 * row]);
-    const float4* src = reinterpret_cast<const float4*>(grad_out + row * channels);
-    float4* dst = reinterpret_cast<float4*>(grad_memory + row * channels);
-    for (int i = lane; i < quads; i += 32)
-      stg_stream(dst + i, keep ? ldg_stream(src + i) : make_float4(0.f, 0.f, 0.f, 0.f));
+    copy_row_or_zero(reinterpret_cast<const float4*>(grad_out + row * channels),
+                     reinterpret_cast<float4*>(grad_memory + row * channels), quads, lane, keep);
   }
 }
 

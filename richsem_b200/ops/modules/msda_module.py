@@ -19,6 +19,7 @@ from torch import nn
 import os
 
 from ... import MultiScaleDeformableAttention as _ext
+from ... import _capi
 from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, prepare_value
 
 
@@ -97,7 +98,12 @@ class MSDeformAttn(nn.Module):
         """
         n, len_q, _ = query.shape
         n, len_in, _ = input_flatten.shape
-        assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == len_in
+        # ms_deform_attn.py:92 reads the device tensor here (a device->host sync per call, and illegal under CUDA-graph
+        # capture); the same check runs on the cached host mirror of the level table
+        if input_spatial_shapes.is_cuda:
+            assert _capi.level_meta(input_spatial_shapes, input_level_start_index).spatial_size_sum == len_in
+        else:
+            assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == len_in
 
         heads, levels, points = self.n_heads, self.n_levels, self.n_points
         # ms_deform_attn.py:94-97: projection, padded tokens zeroed, (N, S, M, D) view — the zeroing (in place for

@@ -185,3 +185,43 @@ def test_proposals_fully_padded_image_and_errors():
     wh = torch.zeros(2, device="cuda", requires_grad=True)
     with pytest.raises(NotImplementedError):
         gen_encoder_output_proposals(memory.cuda(), mask.cuda(), torch.as_tensor(shapes).cuda(), wh)
+
+
+# ---- encoder stack + CUDA graph (8f-3) --------------------------------------------------------------
+@pytest.mark.parametrize("padding", [False, True])
+def test_graphed_encoder_step_matches_eager(padding):
+    """The 6-layer encoder's forward + backward captured in one CUDA graph reproduces the eager step (same kernels;
+    grad_value atomics reorder between runs, hence a tolerance), and new inputs flow through the static buffers."""
+    from richsem_b200 import synthetic as syn
+    from richsem_b200.encoder_layer import DeformableEncoder, GraphedTrainStep
+
+    shapes = [(40, 54), (20, 27), (10, 14), (5, 7)]
+    dev = "cuda:0"
+    shp, starts, S = syn.level_tensors(shapes, dev)
+    torch.manual_seed(3)
+    model = DeformableEncoder(3).to(dev)
+    with torch.no_grad():
+        for layer in model.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+    valid = torch.ones(2, 4, 2, device=dev)
+    mask = None
+    if padding:
+        mask = torch.stack([_rect(shapes, (1.0, 1.0)), _rect(shapes, (0.7, 0.55))]).to(dev)
+        valid[1, :, 0], valid[1, :, 1] = 0.55, 0.7
+    loss_fn = lambda out: out.square().mean()
+    src0, pos = torch.randn(2, S, 256, device=dev), torch.randn(2, S, 256, device=dev)
+    step = GraphedTrainStep(model, loss_fn, (src0, pos, shp, starts, valid, mask))
+    for seed in (1, 2):
+        src = torch.randn(2, S, 256, device=dev, generator=torch.Generator(device=dev).manual_seed(seed))
+        loss = step(src, pos, shp, starts, valid, mask).clone()
+        got = [p.grad.clone() for p in model.parameters()]
+        for p in model.parameters():
+            p.grad = None
+        want_loss = loss_fn(model(src, pos, shp, starts, valid, mask))
+        want_loss.backward()
+        assert abs(loss.item() - want_loss.item()) <= 1e-5 * abs(want_loss.item())
+        for g, p in zip(got, model.parameters()):
+            assert rel_err(g, p.grad) < 1e-4
+        for p in model.parameters():
+            p.grad = None

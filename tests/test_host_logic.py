@@ -141,3 +141,22 @@ def test_install_as_reference_extension():
     assert MSDA.ms_deform_attn_forward is ext.ms_deform_attn_forward
     assert MSDA.ms_deform_attn_backward is ext.ms_deform_attn_backward
     sys.modules.pop("MultiScaleDeformableAttention")
+
+
+def test_encoder_reference_points_match_the_linspace_formulation():
+    """get_reference_points restates deformable_transformer.py:512-525 (meshgrid of linspace(0.5, H-0.5, H)) with
+    index arithmetic; both must give the same bits."""
+    from richsem_b200.encoder_layer import get_reference_points
+
+    shapes = [(13, 21), (7, 11), (4, 6), (2, 3)]
+    vr = torch.tensor([[[1.0, 1.0]] * 4, [[0.7, 0.55], [0.72, 0.5], [0.75, 0.6], [1.0, 0.5]]])
+    refs = []
+    for lvl, (h, w) in enumerate(shapes):
+        ry, rx = torch.meshgrid(torch.linspace(0.5, h - 0.5, h), torch.linspace(0.5, w - 0.5, w), indexing="ij")
+        ry = ry.reshape(-1)[None] / (vr[:, None, lvl, 1] * h)
+        rx = rx.reshape(-1)[None] / (vr[:, None, lvl, 0] * w)
+        refs.append(torch.stack((rx, ry), -1))
+    want = torch.cat(refs, 1)[:, :, None] * vr[:, None]
+    got = get_reference_points(shapes, vr)
+    assert got.shape == (2, sum(h * w for h, w in shapes), 4, 2)
+    assert torch.equal(got, want)
