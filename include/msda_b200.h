@@ -198,7 +198,8 @@ int msda_zero_masked_rows_f32(msda_stream_t stream, float* data, const uint8_t* 
  *   wh_base           DEVICE float[2] = sigmoid(learnedwh) (utils.py:41), or NULL for the constant 0.05 (:43)
  *   output_memory     [batch, spatial_size, channels]: memory, zero on padded or invalid tokens (:54-56)
  *   output_proposals  [batch, spatial_size, 4]: logit of (cx, cy, w, h), +inf on padded or invalid tokens (:49-52)
- *   valid_hw_workspace  DEVICE int32[batch * num_levels * 2], needed when padding_mask != NULL (valid H / W, :27-28)
+ *   valid_hw_workspace  DEVICE int32[batch * num_levels * 2] for the valid H / W (:27-28); only needed with a
+ *                     padding mask and batch * num_levels > 128 (smaller tables are recomputed inside the kernel)
  * The backward routes grad_output_memory to the kept tokens (those whose proposal is finite). */
 int msda_encoder_proposals_f32(msda_stream_t stream, const float* memory, const uint8_t* padding_mask,
                                const int64_t* spatial_shapes, const float* wh_base, int batch, int spatial_size,

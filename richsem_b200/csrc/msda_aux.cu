@@ -134,11 +134,8 @@ struct AuxLevels {
 
 // valid_hw[(b*L + l)*2 + {0,1}] = (#unmasked tokens in the first column, #unmasked tokens in the first row)
 // of level l of image b (utils.py:27-28).  One warp per (image, level).
-__global__ void msda_valid_hw_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ valid_hw,
-                                     const __grid_constant__ AuxLevels lv, int batch, int spatial_size) {
-  const int lane = threadIdx.x & 31;
-  const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (task >= batch * lv.num_levels) return;
+__device__ __forceinline__ int2 valid_hw_of(const uint8_t* __restrict__ mask, const AuxLevels& lv, int task,
+                                            int spatial_size, int lane) {
   const int b = task / lv.num_levels, l = task - b * lv.num_levels;
   const int H = lv.H[l], W = lv.W[l];
   const uint8_t* m = mask + (long long)b * spatial_size + lv.start[l];
@@ -149,11 +146,23 @@ __global__ void msda_valid_hw_kernel(const uint8_t* __restrict__ mask, int32_t* 
     vh += __shfl_xor_sync(0xffffffffu, vh, o);
     vw += __shfl_xor_sync(0xffffffffu, vw, o);
   }
+  return make_int2(vh, vw);
+}
+
+// Stand-alone pass for batches too large for the in-block table of msda_proposals_kernel.
+__global__ void msda_valid_hw_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ valid_hw,
+                                     const __grid_constant__ AuxLevels lv, int batch, int spatial_size) {
+  const int lane = threadIdx.x & 31;
+  const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (task >= batch * lv.num_levels) return;
+  const int2 v = valid_hw_of(mask, lv, task, spatial_size, lane);
   if (lane == 0) {
-    valid_hw[2 * task] = vh;
-    valid_hw[2 * task + 1] = vw;
+    valid_hw[2 * task] = v.x;
+    valid_hw[2 * task + 1] = v.y;
   }
 }
+
+constexpr int kValidInBlock = 128;  // (image, level) pairs a block recomputes for itself (L2-resident mask bytes)
 
 // One warp per token: proposal (cx, cy, w, h) of utils.py:30-46 in logit space (:50-52), validity test (:49),
 // masked copy of the memory row (:54-56).  Same fp32 operations in the same order as the PyTorch expressions.
@@ -170,6 +179,21 @@ msda_proposals_kernel(const float* __restrict__ memory, const uint8_t* __restric
   const float base_w = wh_base ? wh_base[0] : 0.05f;
   const float base_h = wh_base ? wh_base[1] : 0.05f;
   const float inf = __int_as_float(0x7f800000);
+  // valid H / W of every (image, level): small batches recompute the table per block (a few hundred mask bytes out of
+  // L2) instead of waiting for a separate launch; large ones read the table msda_valid_hw_kernel left in valid_hw
+  __shared__ int s_valid[2 * kValidInBlock];
+  const int pairs = batch * lv.num_levels;
+  const bool in_block = mask != nullptr && pairs <= kValidInBlock;
+  if (in_block) {
+    for (int task = threadIdx.x >> 5; task < pairs; task += kAuxThreads / 32) {
+      const int2 v = valid_hw_of(mask, lv, task, spatial_size, lane);
+      if (lane == 0) {
+        s_valid[2 * task] = v.x;
+        s_valid[2 * task + 1] = v.y;
+      }
+    }
+    __syncthreads();
+  }
   for (long long row = warp0; row < rows; row += nwarps) {
     const int b = (int)(row / spatial_size);
     const int s = (int)(row - (long long)b * spatial_size);
@@ -183,8 +207,9 @@ msda_proposals_kernel(const float* __restrict__ memory, const uint8_t* __restric
     bool masked = false;
     if (mask != nullptr) {
       masked = mask[row] != 0;
-      vh = (float)valid_hw[2 * (b * lv.num_levels + l)];
-      vw = (float)valid_hw[2 * (b * lv.num_levels + l) + 1];
+      const int pair = b * lv.num_levels + l;
+      vh = (float)(in_block ? s_valid[2 * pair] : valid_hw[2 * pair]);
+      vw = (float)(in_block ? s_valid[2 * pair + 1] : valid_hw[2 * pair + 1]);
     }
     const float scale_l = (float)(1 << l);  // 2.0 ** lvl (utils.py:41,43)
     float p[4];
@@ -305,7 +330,7 @@ int msda_encoder_proposals_f32(msda_stream_t stream, const float* memory, const 
   if (!memory || !output_memory || !output_proposals) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
   if (!aligned16(memory) || !aligned16(output_memory) || !aligned16(output_proposals))
     return fail(MSDA_ERR_INVALID_ARGUMENT, "memory / output_memory / output_proposals must be 16-byte aligned");
-  if (padding_mask) {
+  if (padding_mask && batch * num_levels > kValidInBlock) {
     if (!valid_hw_workspace)
       return fail(MSDA_ERR_WORKSPACE, "a padding mask needs valid_hw_workspace (batch * num_levels * 2 int32)");
     const int tasks = batch * num_levels;

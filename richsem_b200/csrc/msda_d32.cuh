@@ -91,6 +91,43 @@ struct RowTraits<__nv_bfloat16> {
   }
 };
 
+// ---- which channels a lane scatters into grad_value --------------------------------------------
+// A row reduction is issued as 16-byte `red.global.add.v4.f32` instructions, and L2 performs it per
+// 32-byte sector.  fp32 rows: the 8 lanes of a group hold 4 consecutive channels each, one instruction
+// covers the 128-byte row in 4 full sectors.  bf16 rows: a lane holds 8 consecutive channels; scattering
+// those as two instructions makes each instruction touch 4 HALF sectors (8 sector operations per row —
+// measured: 7.9 M instead of 4.5 M reduction sectors per decoder layer).  So grad_out is re-dealt once per
+// (query, head): instruction i of lane j covers channels 16 i + 4 j .. + 3, i.e. the 4 lanes of one
+// instruction cover 64 contiguous bytes = 2 full sectors.
+template <typename VT>
+struct ScatterDeal;
+template <>
+struct ScatterDeal<float> {
+  static constexpr int N = 1;
+  static __device__ __forceinline__ void deal(const float (&go)[4], int, unsigned, float (&gs)[4]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) gs[c] = go[c];
+  }
+  static __device__ __forceinline__ int offset(int j, int) { return 4 * j; }
+};
+template <>
+struct ScatterDeal<__nv_bfloat16> {
+  static constexpr int N = 2;
+  static __device__ __forceinline__ void deal(const float (&go)[8], int j, unsigned mask, float (&gs)[8]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int src = 2 * i + (j >> 1);  // lane of the group that holds channels 16 i + 4 j .. + 3
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float lo = __shfl_sync(mask, go[c], src, 4);
+        const float hi = __shfl_sync(mask, go[4 + c], src, 4);
+        gs[4 * i + c] = (j & 1) ? hi : lo;
+      }
+    }
+  }
+  static __device__ __forceinline__ int offset(int j, int i) { return 16 * i + 4 * j; }
+};
+
 template <typename VT, int LP>
 struct D32Cfg {
   static constexpr int G = RowTraits<VT>::G;
@@ -415,7 +452,8 @@ msda_bwd_d32_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ valu
   float4* rec = smem + (warp * Cfg::GPW + g) * Cfg::REC_STRIDE;
   const size_t img = (size_t)b * S * M32 + j * C;
   const VT* value_b = value + img;
-  float* gvalue_b = grad_value + img;
+  float* gvalue_img = grad_value + (size_t)b * S * M32;
+  using SD = ScatterDeal<VT>;
 
 #pragma unroll 1
   for (int pass = 0; pass < Cfg::PASSES; ++pass) {
@@ -430,8 +468,9 @@ msda_bwd_d32_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ valu
     const unsigned amask = __ballot_sync(0xffffffffu, active);
 
     if (active) {
-      float go[C];
+      float go[C], gs[C];
       RT::load_stream(grad_out + qm * 32 + j * C, go);
+      if (kScatter) SD::deal(go, j, amask, gs);
       // points are reduced in blocks of G: lane j ends up owning point (G*blk + j) — the same
       // point it decoded, so it also stores that point's gradients.
 #pragma unroll
@@ -462,8 +501,9 @@ msda_bwd_d32_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ valu
                 if (kScatter) {
                   const float t = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
 #pragma unroll
-                  for (int c = 0; c < C; c += 4)
-                    red_add_f4(gvalue_b + o + c, t * go[c], t * go[c + 1], t * go[c + 2], t * go[c + 3]);
+                  for (int i2 = 0; i2 < SD::N; ++i2)
+                    red_add_f4(gvalue_img + o + SD::offset(j, i2), t * gs[4 * i2], t * gs[4 * i2 + 1],
+                               t * gs[4 * i2 + 2], t * gs[4 * i2 + 3]);
                 }
                 float s = 0.f;
 #pragma unroll
@@ -580,12 +620,14 @@ msda_bwd_d32_split_kernel(const VT* __restrict__ grad_out, const VT* __restrict_
   float4* rec = smem + warp * (LP + 1);
   const size_t img = (size_t)b * S * M32 + j * C;
   const VT* value_b = value + img;
-  float* gvalue_b = grad_value + img;
+  float* gvalue_img = grad_value + (size_t)b * S * M32;
+  using SD = ScatterDeal<VT>;
   const size_t qm = ((size_t)b * Lq + q) * M + m;
   d32_decode_points<32, kL, kP>(loc, attw, qm, lane, m, M, lv, rec);
   __syncwarp();
-  float go[C];
+  float go[C], gs[C];
   RT::load_stream(grad_out + qm * 32 + j * C, go);
+  if (kScatter) SD::deal(go, j, 0xffffffffu, gs);
 #pragma unroll
   for (int i = 0; i < NPG; ++i) {
     const int p = g + GPW * i;
@@ -609,8 +651,9 @@ msda_bwd_d32_split_kernel(const VT* __restrict__ grad_out, const VT* __restrict_
           if (kScatter) {
             const float t = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
 #pragma unroll
-            for (int c = 0; c < C; c += 4)
-              red_add_f4(gvalue_b + o + c, t * go[c], t * go[c + 1], t * go[c + 2], t * go[c + 3]);
+            for (int i2 = 0; i2 < SD::N; ++i2)
+              red_add_f4(gvalue_img + o + SD::offset(j, i2), t * gs[4 * i2], t * gs[4 * i2 + 1], t * gs[4 * i2 + 2],
+                         t * gs[4 * i2 + 3]);
           }
           float sdot = 0.f;
 #pragma unroll

@@ -139,7 +139,8 @@ class EncoderProposalsFunction(Function):
         opts.spatial_shapes_host = ctypes.cast(c_shapes, _capi._i64p)
         out_mem = torch.empty_like(memory)
         out_prop = torch.empty(n, s, 4, dtype=torch.float32, device=memory.device)
-        work = torch.empty(max(1, n * levels * 2), dtype=torch.int32, device=memory.device) if m is not None else None
+        work = (torch.empty(n * levels * 2, dtype=torch.int32, device=memory.device)
+                if m is not None and n * levels > 128 else None)  # small tables are recomputed in the kernel
         if wh_base is not None:
             wh_base = wh_base.detach().to(device=memory.device, dtype=torch.float32).contiguous()
             _require(wh_base.numel() == 2, "learnedwh must have 2 elements")

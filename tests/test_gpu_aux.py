@@ -169,6 +169,15 @@ def test_proposals_dino_shape(frac):
     _check_proposals(memory, mask, DINO, None)
 
 
+def test_proposals_large_batch_uses_the_workspace_table():
+    shapes = [(6, 9), (3, 5), (2, 2)]
+    g = torch.Generator().manual_seed(8)
+    n = 50   # 150 (image, level) pairs > 128: valid H / W come from the stand-alone pass
+    memory = torch.randn(n, 73, 8, generator=g)
+    mask = torch.stack([_rect(shapes, (1.0, 1.0) if i % 3 == 0 else (0.3 + 0.01 * i, 0.9 - 0.01 * i)) for i in range(n)])
+    _check_proposals(memory, mask, shapes, None)
+
+
 def test_proposals_fully_padded_image_and_errors():
     from richsem_b200.ops.functions import gen_encoder_output_proposals
 
