@@ -72,7 +72,7 @@ def parse_args():
     ap.add_argument("--padding", action="store_true", help="encoder_stack6: image 1 of each pair is padded (mask path)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=12)
     return ap.parse_args()
 
 
@@ -529,6 +529,7 @@ def run_e2e(args, torch, dist, ext, sets, shp, st, flags, world, dev, queries_pe
     h2d, d2h, comp = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
     h2d_bytes = sum(t.numel() * t.element_size() for hi in host_in for t in hi.values())
     counter = [0]
+    d2h_done = []
 
     def e2e_step():
         nonlocal host_out
@@ -538,6 +539,11 @@ def run_e2e(args, torch, dist, ext, sets, shp, st, flags, world, dev, queries_pe
         dev_in = dev_gen[g]
         if gen_free[g] is not None:
             h2d.wait_event(gen_free[g])
+        # bounded pipeline depth: the HOST does not enqueue step k before the downloads of step k-2 have finished, so
+        # the caching allocator cycles through a fixed set of output blocks (the op allocates its results) instead
+        # of cudaMalloc-ing a new 956 MB set for every step the host runs ahead
+        if len(d2h_done) >= 2:
+            d2h_done[-2].synchronize()
         with torch.cuda.stream(h2d):
             for i in range(layers):
                 for k in names_in:
@@ -565,11 +571,13 @@ def run_e2e(args, torch, dist, ext, sets, shp, st, flags, world, dev, queries_pe
                 d2h.wait_event(ev_b[i])
                 for j in range(3):
                     host_out[i][1 + j].copy_(grads[i][j], non_blocking=True)
+            e = torch.cuda.Event(); e.record(d2h); d2h_done.append(e)
+            del d2h_done[:-2]
         for i in range(layers):  # keep device results alive until the copies are ordered after them
             for t in (outs[i], *grads[i]):
                 t.record_stream(d2h)
 
-    for _ in range(2):
+    for _ in range(4):
         e2e_step()
     if world > 1:
         dist.barrier()
