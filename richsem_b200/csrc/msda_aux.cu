@@ -88,7 +88,9 @@ msda_value_prepare_bf16_kernel(const float* __restrict__ in, const uint8_t* __re
   }
 }
 
-// data[row, :] = 0 where mask[row].  One warp per row; only masked rows are touched.
+// data[row, :] = 0 where mask[row]; only masked rows are touched.  Padding is a rectangle per level, i.e. long runs
+// of masked rows, so rows are dealt to warps round-robin (a warp that owned 32 consecutive rows would do all the
+// work of its run alone: 9 % occupancy in the first version); a warp tests four of its rows per iteration.
 __global__ void __launch_bounds__(kAuxThreads)
 msda_zero_masked_rows_kernel(float* __restrict__ data, const uint8_t* __restrict__ mask, long long rows,
                              int row_elems) {
@@ -96,16 +98,20 @@ msda_zero_masked_rows_kernel(float* __restrict__ data, const uint8_t* __restrict
   const long long warp0 = (long long)blockIdx.x * (kAuxThreads / 32) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (kAuxThreads / 32);
   const int quads = row_elems >> 2;
-  // a warp looks at 32 consecutive mask bytes at once and then zeroes the flagged rows one after another
-  for (long long base = warp0 * 32; base < rows; base += nwarps * 32) {
-    const long long mine = base + lane;
-    const bool flag = mine < rows && mask[mine] != 0;
-    unsigned todo = __ballot_sync(0xffffffffu, flag);
-    while (todo) {
-      const int r = __ffs(todo) - 1;
-      todo &= todo - 1;
-      float4* dst = reinterpret_cast<float4*>(data + (base + r) * row_elems);
-      for (int i = lane; i < quads; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = warp0; row < rows; row += 4 * nwarps) {
+    bool flag[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = row + u * nwarps;
+      flag[u] = r < rows && mask[r] != 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (flag[u]) {
+        float4* dst = reinterpret_cast<float4*>(data + (row + u * nwarps) * row_elems);
+        for (int i = lane; i < quads; i += 32) dst[i] = z;
+      }
     }
   }
 }
@@ -310,7 +316,7 @@ int msda_zero_masked_rows_f32(msda_stream_t stream, float* data, const uint8_t* 
   if (rows == 0) return MSDA_OK;
   if (!data || !padding_mask) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
   if (!aligned16(data)) return fail(MSDA_ERR_INVALID_ARGUMENT, "data must be 16-byte aligned");
-  msda_zero_masked_rows_kernel<<<aux_grid((rows + 31) / 32), kAuxThreads, 0, (cudaStream_t)stream>>>(
+  msda_zero_masked_rows_kernel<<<aux_grid((rows + 3) / 4), kAuxThreads, 0, (cudaStream_t)stream>>>(
       data, padding_mask, rows, row_elems);
   return after_launch("msda_zero_masked_rows_kernel");
 }
