@@ -200,43 +200,65 @@ msda_proposals_kernel(const float* __restrict__ memory, const uint8_t* __restric
     }
     __syncthreads();
   }
-  for (long long row = warp0; row < rows; row += nwarps) {
-    const int b = (int)(row / spatial_size);
-    const int s = (int)(row - (long long)b * spatial_size);
+  // The per-token arithmetic (level lookup, integer division, IEEE divisions, logf) costs ~250 instructions, and with
+  // one token per warp the kernel was bound by instruction issue (69 % of issue slots, 13.4 M warp instructions:
+  // profiles/r1_aux_passes.md).  So a warp takes FOUR tokens at a time, 8 lanes each: the arithmetic is SIMT-shared
+  // between the four, and a lane moves 8 x 16 bytes of its row (all loads ahead of the stores) at 256 channels.
+  constexpr int kLanesPerRow = 8, kRowsPerWarp = 32 / kLanesPerRow;
+  const int sub = lane / kLanesPerRow, j = lane % kLanesPerRow;
+  const long long first = warp0 * kRowsPerWarp + sub;
+  const long long stride = nwarps * kRowsPerWarp;
+  // (image, token) of this lane group's row, advanced incrementally (no 64-bit division per row)
+  int b = (int)(first / spatial_size);
+  int s = (int)(first - (long long)b * spatial_size);
+  const int step_b = (int)(stride / spatial_size), step_s = (int)(stride - (long long)step_b * spatial_size);
+  for (long long row0 = warp0 * kRowsPerWarp; row0 < rows; row0 += stride) {
+    const long long row = row0 + sub;
+    const bool live = row < rows;
     int l = 0;
 #pragma unroll 1
     for (int k = 1; k < lv.num_levels; ++k) l += s >= lv.start[k];
     const int W = lv.W[l];
     const int rel = s - lv.start[l];
-    const int y = rel / W, x = rel - y * W;
+    const int y = (int)((unsigned)rel / (unsigned)W), x = rel - y * W;
     float vw = (float)W, vh = (float)lv.H[l];
     bool masked = false;
-    if (mask != nullptr) {
+    if (mask != nullptr && live) {
       masked = mask[row] != 0;
       const int pair = b * lv.num_levels + l;
       vh = (float)(in_block ? s_valid[2 * pair] : valid_hw[2 * pair]);
       vw = (float)(in_block ? s_valid[2 * pair + 1] : valid_hw[2 * pair + 1]);
     }
     const float scale_l = (float)(1 << l);  // 2.0 ** lvl (utils.py:41,43)
-    float p[4];
-    p[0] = __fdiv_rn((float)x + 0.5f, vw);
-    p[1] = __fdiv_rn((float)y + 0.5f, vh);
-    p[2] = __fmul_rn(base_w, scale_l);
-    p[3] = __fmul_rn(base_h, scale_l);
-    bool valid = true;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) valid = valid && (p[k] > 0.01f) && (p[k] < 0.99f);
+    // lanes 0..3 of a group take one component each: cx, cy, w, h
+    const int comp = j & 3;
+    const float centre = __fdiv_rn((float)(comp == 0 ? x : y) + 0.5f, comp == 0 ? vw : vh);  // one division per lane
+    const float extent = __fmul_rn(comp == 2 ? base_w : base_h, scale_l);
+    const float pk = comp < 2 ? centre : extent;
+    const bool ok = (pk > 0.01f) && (pk < 0.99f);
+    const bool valid = ((__ballot_sync(0xffffffffu, ok) >> (sub * kLanesPerRow)) & 0xfu) == 0xfu;
     const bool keep = valid && !masked;
-    if (lane == 0) {
-      float4 o;
-      o.x = keep ? logf(__fdiv_rn(p[0], __fsub_rn(1.f, p[0]))) : inf;
-      o.y = keep ? logf(__fdiv_rn(p[1], __fsub_rn(1.f, p[1]))) : inf;
-      o.z = keep ? logf(__fdiv_rn(p[2], __fsub_rn(1.f, p[2]))) : inf;
-      o.w = keep ? logf(__fdiv_rn(p[3], __fsub_rn(1.f, p[3]))) : inf;
-      stg_stream(reinterpret_cast<float4*>(out_proposals) + row, o);
+    if (live) {
+      if (j < 4) out_proposals[4 * row + j] = keep ? logf(__fdiv_rn(pk, __fsub_rn(1.f, pk))) : inf;
+      const float4* src = reinterpret_cast<const float4*>(memory + row * channels);
+      float4* dst = reinterpret_cast<float4*>(out_memory + row * channels);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = j; i < quads; i += 8 * kLanesPerRow) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v[u] = (keep && i + kLanesPerRow * u < quads) ? ldg_stream(src + i + kLanesPerRow * u) : z;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (i + kLanesPerRow * u < quads) stg_stream(dst + i + kLanesPerRow * u, v[u]);
+      }
     }
-    copy_row_or_zero(reinterpret_cast<const float4*>(memory + row * channels),
-                     reinterpret_cast<float4*>(out_memory + row * channels), quads, lane, keep);
+    b += step_b;
+    s += step_s;
+    if (s >= spatial_size) {
+      s -= spatial_size;
+      ++b;
+    }
   }
 }
 
@@ -344,7 +366,7 @@ int msda_encoder_proposals_f32(msda_stream_t stream, const float* memory, const 
     const int rc2 = after_launch("msda_valid_hw_kernel");
     if (rc2 != MSDA_OK) return rc2;
   }
-  msda_proposals_kernel<<<aux_grid((long long)batch * spatial_size), kAuxThreads, 0, s>>>(
+  msda_proposals_kernel<<<aux_grid(((long long)batch * spatial_size + 3) / 4), kAuxThreads, 0, s>>>(
       memory, padding_mask, valid_hw_workspace, wh_base, output_memory, output_proposals, lv, batch, spatial_size,
       channels);
   return after_launch("msda_proposals_kernel");
