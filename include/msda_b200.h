@@ -209,6 +209,18 @@ int msda_encoder_proposals_backward_f32(msda_stream_t stream, const float* grad_
                                         const float* output_proposals, int batch, int spatial_size, int channels,
                                         float* grad_memory);
 
+/* ---- two-stage query selection (second half) -----------
+ * models/richsem/deformable_transformer.py:367-369:
+ *   topk_proposals = torch.topk(enc_outputs_class_unselected.max(-1)[0], num_queries, dim=1)[1]
+ * msda_rowmax_f32     scores[row] = max_c logits[row, c]   (logits [rows, num_classes]; a NaN in a row gives NaN)
+ * msda_topk_rows_f32  indices[b, :] = positions of the k largest scores of row b of scores [batch, row_len], sorted by
+ *                     descending score; equal scores: lower index first; NaN ranks above everything (torch.topk).
+ *                     indices int64 [batch, k]; values (optional, may be NULL) fp32 [batch, k].  k <= 1024, else
+ *                     MSDA_ERR_UNSUPPORTED. */
+int msda_rowmax_f32(msda_stream_t stream, const float* logits, long long rows, int num_classes, float* scores);
+int msda_topk_rows_f32(msda_stream_t stream, const float* scores, int batch, int row_len, int k, int64_t* indices,
+                       float* values);
+
 /* ---- index contract probe --------------------------------------------------
  * Writes, for every sample (b,q,m,l,p), the four bilinear corner token indices
  * (level_start_index[l] + h*W_l + w, i.e. an index into the spatial_size axis)

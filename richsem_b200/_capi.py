@@ -86,6 +86,10 @@ def _load():
     lib.msda_encoder_proposals_f32.restype = _i
     lib.msda_encoder_proposals_backward_f32.argtypes = [_vp, _vp, _vp, _i, _i, _i, _vp]
     lib.msda_encoder_proposals_backward_f32.restype = _i
+    lib.msda_rowmax_f32.argtypes = [_vp, _vp, _ll, _i, _vp]
+    lib.msda_rowmax_f32.restype = _i
+    lib.msda_topk_rows_f32.argtypes = [_vp, _vp, _i, _i, _i, _vp, _vp]
+    lib.msda_topk_rows_f32.restype = _i
     lib.msda_debug_corners_f32.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, opts_p]
     lib.msda_debug_corners_f32.restype = _i
     lib.msda_backward_workspace_bytes.argtypes = [_i] * 7

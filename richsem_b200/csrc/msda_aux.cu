@@ -390,3 +390,212 @@ int msda_encoder_proposals_backward_f32(msda_stream_t stream, const float* grad_
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Two-stage query selection (second half): models/richsem/deformable_transformer.py:367-369
+//   topk_proposals = torch.topk(enc_outputs_class_unselected.max(-1)[0], num_queries, dim=1)[1]
+// msda_rowmax_f32: scores[row] = max over the class logits of a token (HBM-bound: reads rows x K floats once).
+// msda_topk_rows_f32: per image, the indices of the k largest scores, sorted by descending score (ties: lower
+// index first; NaN counts as the largest value, like torch.topk) — one thread block per image: 4-pass 8-bit radix
+// select of the k-th key over the L2-resident scores, ordered collection, bitonic sort of the k winners.
+// =====================================================================================================
+namespace {
+
+__device__ __forceinline__ float ldg_stream_f1(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// torch.max semantics: a NaN anywhere in the row makes the result NaN.
+__device__ __forceinline__ float max_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
+
+__global__ void __launch_bounds__(kAuxThreads)
+msda_rowmax_kernel(const float* __restrict__ logits, float* __restrict__ scores, long long rows, int K) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (kAuxThreads / 32) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (kAuxThreads / 32);
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float* src = logits + row * K;
+    float m = -INFINITY;
+    int i = lane;
+    for (; i + 224 < K; i += 256) {  // eight coalesced 128-byte loads in flight per warp
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = ldg_stream_f1(src + i + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) m = max_nan(m, v[u]);
+    }
+    for (; i < K; i += 32) m = max_nan(m, ldg_stream_f1(src + i));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = max_nan(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) scores[row] = m;
+  }
+}
+
+// Monotone map float -> uint32 (larger float = larger key); every NaN maps to the largest key.
+__device__ __forceinline__ unsigned topk_key(float f) {
+  if (f != f) return 0xffffffffu;
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+constexpr int kTopkThreads = 1024;
+constexpr int kTopkMax = 1024;
+
+__global__ void __launch_bounds__(kTopkThreads)
+msda_topk_rows_kernel(const float* __restrict__ scores, long long* __restrict__ indices, float* __restrict__ values,
+                      int row_len, int k) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_want, s_count_gt, s_tie_base;
+  __shared__ unsigned s_warp_sum[kTopkThreads / 32];
+  __shared__ unsigned long long s_list[kTopkMax];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = scores + (long long)blockIdx.x * row_len;
+
+  // ---- radix select: key of the k-th largest element ------------------------------------------------
+  if (tid == 0) {
+    s_prefix = 0u;
+    s_want = (unsigned)k;
+  }
+  unsigned prefix_mask = 0u;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (tid < 256) hist[tid] = 0u;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    for (int i = tid; i < row_len; i += kTopkThreads) {
+      const unsigned key = topk_key(row[i]);
+      if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // lane l owns bins 8l .. 8l+7; suffix sums from the top bin down
+      unsigned h[8], mine = 0u;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        h[b] = hist[8 * lane + b];
+        mine += h[b];
+      }
+      // inclusive suffix sum over the lanes: elements in this lane's bins and in all higher bins
+      unsigned suffix = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_down_sync(0xffffffffu, suffix, o);
+        if (lane + o < 32) suffix += t;
+      }
+      const unsigned above = suffix - mine;
+      const unsigned want = s_want;
+      if (above < want && want <= suffix) {  // the k-th element falls into one of this lane's bins (exactly one lane)
+        unsigned cum = above, cum_at = 0u;
+        int chosen = -1;
+#pragma unroll
+        for (int b = 7; b >= 0; --b) {
+          if (chosen < 0) {
+            if (want <= cum + h[b]) {
+              chosen = b;
+              cum_at = cum;
+            } else {
+              cum += h[b];
+            }
+          }
+        }
+        s_prefix = prefix | ((unsigned)(8 * lane + chosen) << shift);
+        s_want = want - cum_at;
+      }
+    }
+    prefix_mask |= 255u << shift;
+    __syncthreads();
+  }
+  const unsigned T = s_prefix;      // key of the k-th largest element
+  const unsigned ties = s_want;     // how many elements equal to T belong to the top k
+  const unsigned n_gt = (unsigned)k - ties;
+
+  // ---- collection: everything above T, and the first `ties` elements equal to T in index order -------
+  if (tid == 0) {
+    s_count_gt = 0u;
+    s_tie_base = 0u;
+  }
+  for (int e = tid; e < kTopkMax; e += kTopkThreads) s_list[e] = 0ull;
+  __syncthreads();
+  for (int i0 = 0; i0 < row_len; i0 += kTopkThreads) {
+    const int i = i0 + tid;
+    unsigned key = 0u;
+    bool gt = false, eq = false;
+    if (i < row_len) {
+      key = topk_key(row[i]);
+      gt = key > T;
+      eq = key == T;
+    }
+    if (gt) {
+      const unsigned slot = atomicAdd(&s_count_gt, 1u);
+      s_list[slot] = ((unsigned long long)key << 32) | (0xffffffffu - (unsigned)i);
+    }
+    // ordered rank among the elements equal to T
+    const unsigned bal = __ballot_sync(0xffffffffu, eq);
+    const unsigned before = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) s_warp_sum[warp] = __popc(bal);
+    __syncthreads();
+    unsigned base = s_tie_base;
+    for (int w = 0; w < warp; ++w) base += s_warp_sum[w];
+    if (eq) {
+      const unsigned r = base + before;
+      if (r < ties) s_list[n_gt + r] = ((unsigned long long)key << 32) | (0xffffffffu - (unsigned)i);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned tot = 0u;
+      for (int w = 0; w < kTopkThreads / 32; ++w) tot += s_warp_sum[w];
+      s_tie_base += tot;
+    }
+    __syncthreads();
+  }
+
+  // ---- bitonic sort, descending by (key, -index) ------------------------------------------------------
+  for (int size = 2; size <= kTopkMax; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int partner = tid ^ stride;
+      if (partner > tid) {
+        const unsigned long long a = s_list[tid], b = s_list[partner];
+        const bool desc = (tid & size) == 0;
+        if (desc ? (a < b) : (a > b)) {
+          s_list[tid] = b;
+          s_list[partner] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid < k) {
+    const unsigned long long e = s_list[tid];
+    const unsigned idx = 0xffffffffu - (unsigned)(e & 0xffffffffull);
+    indices[(long long)blockIdx.x * k + tid] = (long long)idx;
+    if (values != nullptr) values[(long long)blockIdx.x * k + tid] = row[idx];
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int msda_rowmax_f32(msda_stream_t stream, const float* logits, long long rows, int num_classes, float* scores) {
+  if (rows < 0 || num_classes < 1)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "rows=%lld num_classes=%d", rows, num_classes);
+  if (rows == 0) return MSDA_OK;
+  if (!logits || !scores) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  msda_rowmax_kernel<<<aux_grid(rows), kAuxThreads, 0, (cudaStream_t)stream>>>(logits, scores, rows, num_classes);
+  return after_launch("msda_rowmax_kernel");
+}
+
+int msda_topk_rows_f32(msda_stream_t stream, const float* scores, int batch, int row_len, int k, int64_t* indices,
+                       float* values) {
+  if (batch < 0 || row_len < 1 || k < 1 || k > row_len)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "batch=%d row_len=%d k=%d", batch, row_len, k);
+  if (k > kTopkMax) return fail(MSDA_ERR_UNSUPPORTED, "k=%d: at most %d winners per row", k, kTopkMax);
+  if (batch == 0) return MSDA_OK;
+  if (!scores || !indices) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64 indices");
+  msda_topk_rows_kernel<<<batch, kTopkThreads, 0, (cudaStream_t)stream>>>(
+      scores, reinterpret_cast<long long*>(indices), values, row_len, k);
+  return after_launch("msda_topk_rows_kernel");
+}
+
+}  // extern "C"

@@ -181,3 +181,41 @@ def gen_encoder_output_proposals(memory, memory_padding_mask, spatial_shapes, le
             raise NotImplementedError("gen_encoder_output_proposals: no gradient for learnedwh on the B200 path")
         wh_base = learnedwh.detach().sigmoid()
     return EncoderProposalsFunction.apply(memory, memory_padding_mask, spatial_shapes, wh_base)
+
+
+def class_scores(enc_outputs_class: torch.Tensor) -> torch.Tensor:
+    """``enc_outputs_class.max(-1)[0]`` (deformable_transformer.py:369) — (N, S, K) fp32 -> (N, S)."""
+    if not enc_outputs_class.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    _require(enc_outputs_class.dtype == torch.float32 and enc_outputs_class.dim() >= 2, "class logits must be fp32 (..., K)")
+    x = enc_outputs_class.detach().contiguous()
+    out = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
+    rows = out.numel()
+    with _on_device(x.device):
+        _capi.check(_capi.lib.msda_rowmax_f32(_stream(x.device), x.data_ptr(), rows, x.shape[-1], out.data_ptr()),
+                    "msda_rowmax_f32")
+    return out
+
+
+def topk_rows(scores: torch.Tensor, k: int, return_values: bool = False):
+    """``torch.topk(scores, k, dim=1)[1]`` for (N, S) fp32 scores: (N, k) int64, sorted by descending score (equal
+    scores: lower index first).  k <= 1024."""
+    if not scores.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    _require(scores.dtype == torch.float32 and scores.dim() == 2, "scores must be (N, S) fp32")
+    _require(1 <= k <= scores.shape[1], f"selected index k out of range: k={k}, row length {scores.shape[1]}")
+    s = scores.detach().contiguous()
+    idx = torch.empty(s.shape[0], k, dtype=torch.int64, device=s.device)
+    val = torch.empty(s.shape[0], k, dtype=torch.float32, device=s.device) if return_values else None
+    with _on_device(s.device):
+        _capi.check(_capi.lib.msda_topk_rows_f32(_stream(s.device), s.data_ptr(), s.shape[0], s.shape[1], k,
+                                                 idx.data_ptr(), None if val is None else val.data_ptr()),
+                    "msda_topk_rows_f32")
+    return (val, idx) if return_values else idx
+
+
+def topk_proposals(enc_outputs_class: torch.Tensor, topk: int) -> torch.Tensor:
+    """deformable_transformer.py:367-369 in two kernels: ``torch.topk(enc_outputs_class.max(-1)[0], topk, dim=1)[1]``
+    — the indices of the ``topk`` tokens with the largest best-class logit, (N, topk) int64.  Not differentiable
+    (indices), like the reference expression."""
+    return topk_rows(class_scores(enc_outputs_class), topk)

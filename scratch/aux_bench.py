@@ -123,6 +123,26 @@ def main():
     tms = timeit([lambda x=x: torch_proposals(x) for x in xs], a.iters)
     report("encoder_proposals_f32", ms, alg, tms, "vs the reference's PyTorch expression sequence (utils.py:10-65)")
 
+    # 8f-4, second half: best-class logit per token + top-900 tokens per image (deformable_transformer.py:367-369)
+    from richsem_b200.ops.functions import topk_proposals
+    from richsem_b200.ops.functions.aux_functions import class_scores, topk_rows
+
+    for kc in (91, 1203):
+        ls = [torch.randn(n, S, kc, device=dev) for _ in range(max(2, min(a.sets, 4)))]
+        alg = rows * kc * 4 + rows * 4
+        ms = timeit([lambda x=x: class_scores(x) for x in ls], a.iters)
+        tms = timeit([lambda x=x: x.max(-1)[0] for x in ls], a.iters)
+        report(f"class_scores_K{kc}", ms, alg, tms, "vs logits.max(-1)[0]")
+        ms = timeit([lambda x=x: topk_proposals(x, 900) for x in ls], a.iters)
+        tms = timeit([lambda x=x: torch.topk(x.max(-1)[0], 900, dim=1)[1] for x in ls], a.iters)
+        report(f"topk_proposals_K{kc}", ms, alg + rows * 4 + n * 900 * 8, tms,
+               "vs torch.topk(logits.max(-1)[0], 900, dim=1)[1]")
+        del ls
+    sc = [torch.randn(n, S, device=dev) for _ in range(4)]
+    ms = timeit([lambda x=x: topk_rows(x, 900) for x in sc], a.iters)
+    tms = timeit([lambda x=x: torch.topk(x, 900, dim=1)[1] for x in sc], a.iters)
+    report("topk_rows_k900", ms, rows * 4 + n * 900 * 8, tms, "vs torch.topk(scores, 900, dim=1)[1] (latency-bound: one block per image)")
+
 
 if __name__ == "__main__":
     main()

@@ -234,3 +234,83 @@ def test_graphed_encoder_step_matches_eager(padding):
             assert rel_err(g, p.grad) < 1e-4
         for p in model.parameters():
             p.grad = None
+
+
+# ---- two-stage query selection (8f-4, second half) ------------------------------------------------------
+@pytest.mark.parametrize("rows_shape,k_classes", [((2, 22223), 91), ((2, 22223), 1203), ((3, 50), 1), ((1, 7), 256), ((2, 300), 31)])
+def test_class_scores_match_torch_max(rows_shape, k_classes):
+    from richsem_b200.ops.functions.aux_functions import class_scores
+
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(*rows_shape, k_classes, generator=g)
+    got = class_scores(x.cuda()).cpu()
+    assert torch.equal(got, x.max(-1)[0])          # a maximum is exact
+
+
+def test_class_scores_propagate_nan_like_torch():
+    from richsem_b200.ops.functions.aux_functions import class_scores
+
+    x = torch.randn(4, 300)
+    x[1, 17] = float("nan")
+    x[2, 299] = float("nan")
+    x[3, 5] = float("inf")
+    got = class_scores(x.cuda()).cpu()
+    want = x.max(-1)[0]
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.equal(got[~torch.isnan(want)], want[~torch.isnan(want)])
+
+
+@pytest.mark.parametrize("n,s,k", [(2, 22223, 900), (2, 22323, 900), (3, 1000, 1000), (1, 5000, 1), (4, 1024, 37), (2, 66450, 1024)])
+def test_topk_rows_matches_torch_topk(n, s, k):
+    from richsem_b200.ops.functions.aux_functions import topk_rows
+
+    g = torch.Generator().manual_seed(41)
+    scores = torch.randn(n, s, generator=g)
+    val, idx = topk_rows(scores.cuda(), k, return_values=True)
+    want_val, want_idx = torch.topk(scores, k, dim=1)
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == (n, k)
+    assert torch.equal(val.cpu(), want_val)                       # the selected scores, in order: bit-exact
+    assert torch.equal(scores.gather(1, idx.cpu()), want_val)     # indices point at them
+    # indices are bit-exact wherever the score is unique in its row (torch leaves the order of ties unspecified)
+    for b in range(n):
+        v = want_val[b]
+        unique = torch.ones(k, dtype=torch.bool)
+        unique[1:] &= v[1:] != v[:-1]
+        unique[:-1] &= v[:-1] != v[1:]
+        kth = v[-1]
+        unique &= ~((v == kth) & ((scores[b] == kth).sum() > (v == kth).sum()))
+        assert torch.equal(idx.cpu()[b][unique], want_idx[b][unique])
+
+
+def test_topk_rows_ties_nan_and_masked_tokens():
+    """Ties are broken towards the lower index; NaN ranks first (torch.topk); a row of mostly equal scores — what the
+    zeroed memory rows of padded tokens produce (utils.py:54-56) — still yields k distinct indices."""
+    from richsem_b200.ops.functions.aux_functions import topk_rows
+
+    s = torch.zeros(2, 5000)
+    s[0, 100:110] = 1.0
+    s[0, 4000] = 2.0
+    s[0, 77] = float("nan")
+    s[1] = -3.0
+    s[1, 4999] = float("inf")
+    s[1, 0] = float("-inf")
+    idx = topk_rows(s.cuda(), 20).cpu()
+    assert idx[0].tolist() == [77, 4000] + list(range(100, 110)) + list(range(0, 8))
+    assert idx[1].tolist() == [4999] + list(range(1, 20))
+    for b in range(2):
+        assert len(set(idx[b].tolist())) == 20
+
+
+def test_topk_proposals_is_the_reference_expression():
+    from richsem_b200.ops.functions import topk_proposals
+
+    g = torch.Generator().manual_seed(43)
+    logits = torch.randn(2, 22223, 91, generator=g)
+    got = topk_proposals(logits.cuda(), 900).cpu()
+    want = torch.topk(logits.max(-1)[0], 900, dim=1)[1]           # deformable_transformer.py:367-369
+    assert torch.equal(logits.max(-1)[0].gather(1, got), logits.max(-1)[0].gather(1, want))
+    assert (got == want).float().mean() > 0.999
+    with pytest.raises(RuntimeError, match="out of range"):
+        topk_proposals(logits.cuda(), 30000)
+    with pytest.raises(RuntimeError, match="at most 1024"):
+        topk_proposals(logits.cuda(), 2000)
