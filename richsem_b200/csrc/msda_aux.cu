@@ -9,7 +9,10 @@
 //
 // All kernels are HBM-bound byte movers: one warp per token row, 16-byte streaming accesses, grid-stride
 // over a grid that is a multiple of the SM count.
+#include <cooperative_groups.h>
+
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "msda_host.h"
@@ -410,26 +413,42 @@ __device__ __forceinline__ float ldg_stream_f1(const float* p) {
 // torch.max semantics: a NaN anywhere in the row makes the result NaN.
 __device__ __forceinline__ float max_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
 
+// kLanes lanes per row (32 / kLanes rows per warp): 32 for wide rows (LVIS: 1203 classes), 8 for narrow ones (COCO: 91),
+// where a whole warp per row would leave most lanes without a 16-byte load.
+template <int kLanes>
 __global__ void __launch_bounds__(kAuxThreads)
 msda_rowmax_kernel(const float* __restrict__ logits, float* __restrict__ scores, long long rows, int K) {
-  const int lane = threadIdx.x & 31;
+  constexpr int kRowsPerWarp = 32 / kLanes;
+  const int lane = threadIdx.x & 31, sub = lane / kLanes, j = lane % kLanes;
   const long long warp0 = (long long)blockIdx.x * (kAuxThreads / 32) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (kAuxThreads / 32);
-  for (long long row = warp0; row < rows; row += nwarps) {
-    const float* src = logits + row * K;
+  for (long long row0 = warp0 * kRowsPerWarp; row0 < rows; row0 += nwarps * kRowsPerWarp) {
+    const long long row = row0 + sub;
     float m = -INFINITY;
-    int i = lane;
-    for (; i + 224 < K; i += 256) {  // eight coalesced 128-byte loads in flight per warp
-      float v[8];
+    if (row < rows) {
+      // K is arbitrary (91, 1203, ...), so rows start at any 4-byte offset: up to 3 scalars in front, then the
+      // 16-byte aligned body with four 16-byte loads in flight per lane, then up to 3 scalars behind
+      const float* src = logits + row * K;
+      int head = (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u) >> 2);
+      head = head < K ? head : K;
+      const int nq = (K - head) >> 2;
+      const int tail0 = head + 4 * nq;
+      if (j < head) m = ldg_stream_f1(src + j);
+      if (j < 3 && tail0 + j < K) m = max_nan(m, ldg_stream_f1(src + tail0 + j));
+      const float4* body = reinterpret_cast<const float4*>(src + head);
+      for (int i = j; i < nq; i += 4 * kLanes) {
+        float4 v[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = ldg_stream_f1(src + i + 32 * u);
+        for (int u = 0; u < 4; ++u)
+          v[u] = (i + kLanes * u < nq) ? ldg_stream(body + i + kLanes * u)
+                                       : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) m = max_nan(m, v[u]);
+        for (int u = 0; u < 4; ++u) m = max_nan(max_nan(m, max_nan(v[u].x, v[u].y)), max_nan(v[u].z, v[u].w));
+      }
     }
-    for (; i < K; i += 32) m = max_nan(m, ldg_stream_f1(src + i));
 #pragma unroll
-    for (int o = 16; o; o >>= 1) m = max_nan(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) scores[row] = m;
+    for (int o = kLanes / 2; o; o >>= 1) m = max_nan(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (j == 0 && row < rows) scores[row] = m;
   }
 }
 
@@ -442,16 +461,29 @@ __device__ __forceinline__ unsigned topk_key(float f) {
 
 constexpr int kTopkThreads = 1024;
 constexpr int kTopkMax = 1024;
+constexpr int kTopkStageMax = 49152;  // keys of one row staged in shared memory (192 KB of the 227 KB)
 
 __global__ void __launch_bounds__(kTopkThreads)
 msda_topk_rows_kernel(const float* __restrict__ scores, long long* __restrict__ indices, float* __restrict__ values,
-                      int row_len, int k) {
+                      int row_len, int k, bool staged) {
   __shared__ unsigned hist[256];
   __shared__ unsigned s_prefix, s_want, s_count_gt, s_tie_base;
   __shared__ unsigned s_warp_sum[kTopkThreads / 32];
   __shared__ unsigned long long s_list[kTopkMax];
+  extern __shared__ unsigned s_keys[];  // staged == true: the row's keys (the five passes below then never leave the SM)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* row = scores + (long long)blockIdx.x * row_len;
+  if (staged) {
+    for (int i = tid; i < row_len; i += 4 * kTopkThreads) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (i + u * kTopkThreads < row_len) ? row[i + u * kTopkThreads] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * kTopkThreads < row_len) s_keys[i + u * kTopkThreads] = topk_key(v[u]);
+    }
+    __syncthreads();
+  }
 
   // ---- radix select: key of the k-th largest element ------------------------------------------------
   if (tid == 0) {
@@ -463,9 +495,17 @@ msda_topk_rows_kernel(const float* __restrict__ scores, long long* __restrict__ 
     if (tid < 256) hist[tid] = 0u;
     __syncthreads();
     const unsigned prefix = s_prefix;
-    for (int i = tid; i < row_len; i += kTopkThreads) {
-      const unsigned key = topk_key(row[i]);
-      if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    for (int i0 = 0; i0 < row_len; i0 += kTopkThreads) {  // uniform trip count: whole warps reach the match
+      const int i = i0 + tid;
+      unsigned bin = 256u;  // "not a candidate"
+      if (i < row_len) {
+        const unsigned key = staged ? s_keys[i] : topk_key(row[i]);
+        if ((key & prefix_mask) == prefix) bin = (key >> shift) & 255u;
+      }
+      // scores cluster in a few exponent bins, so the lanes of a warp mostly hit the same counter: one atomic per
+      // distinct bin and warp
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (bin < 256u && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
     }
     __syncthreads();
     if (warp == 0) {
@@ -485,6 +525,7 @@ msda_topk_rows_kernel(const float* __restrict__ scores, long long* __restrict__ 
       }
       const unsigned above = suffix - mine;
       const unsigned want = s_want;
+      __syncwarp();  // every lane has read s_want before the owning lane rewrites it
       if (above < want && want <= suffix) {  // the k-th element falls into one of this lane's bins (exactly one lane)
         unsigned cum = above, cum_at = 0u;
         int chosen = -1;
@@ -522,7 +563,7 @@ msda_topk_rows_kernel(const float* __restrict__ scores, long long* __restrict__ 
     unsigned key = 0u;
     bool gt = false, eq = false;
     if (i < row_len) {
-      key = topk_key(row[i]);
+      key = staged ? s_keys[i] : topk_key(row[i]);
       gt = key > T;
       eq = key == T;
     }
@@ -530,7 +571,9 @@ msda_topk_rows_kernel(const float* __restrict__ scores, long long* __restrict__ 
       const unsigned slot = atomicAdd(&s_count_gt, 1u);
       s_list[slot] = ((unsigned long long)key << 32) | (0xffffffffu - (unsigned)i);
     }
-    // ordered rank among the elements equal to T
+    // ordered rank among the elements equal to T (rare: one barrier tells whether this chunk has any)
+    const int chunk_ties = __syncthreads_count(eq);
+    if (chunk_ties == 0 || s_tie_base >= ties) continue;   // uniform: both operands are block-wide values
     const unsigned bal = __ballot_sync(0xffffffffu, eq);
     const unsigned before = __popc(bal & ((1u << lane) - 1u));
     if (lane == 0) s_warp_sum[warp] = __popc(bal);
@@ -542,34 +585,225 @@ msda_topk_rows_kernel(const float* __restrict__ scores, long long* __restrict__ 
       if (r < ties) s_list[n_gt + r] = ((unsigned long long)key << 32) | (0xffffffffu - (unsigned)i);
     }
     __syncthreads();
-    if (tid == 0) {
-      unsigned tot = 0u;
-      for (int w = 0; w < kTopkThreads / 32; ++w) tot += s_warp_sum[w];
-      s_tie_base += tot;
-    }
+    if (tid == 0) s_tie_base += (unsigned)chunk_ties;
     __syncthreads();
   }
+  __syncthreads();
 
   // ---- bitonic sort, descending by (key, -index) ------------------------------------------------------
+  // (the element lives in a register; partners less than a warp apart are exchanged with shuffles, so only 15 of the
+  // 55 compare-exchange stages need shared memory and barriers)
+  unsigned long long v = s_list[tid];
   for (int size = 2; size <= kTopkMax; size <<= 1) {
+    const bool desc = (tid & size) == 0;
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      const int partner = tid ^ stride;
-      if (partner > tid) {
-        const unsigned long long a = s_list[tid], b = s_list[partner];
-        const bool desc = (tid & size) == 0;
-        if (desc ? (a < b) : (a > b)) {
-          s_list[tid] = b;
-          s_list[partner] = a;
-        }
+      unsigned long long other;
+      if (stride >= 32) {
+        s_list[tid] = v;
+        __syncthreads();
+        other = s_list[tid ^ stride];
+        __syncthreads();
+      } else {
+        other = __shfl_xor_sync(0xffffffffu, v, stride);
       }
-      __syncthreads();
+      const bool lower = (tid & stride) == 0;
+      const bool keep_max = lower == desc;
+      v = keep_max ? (v > other ? v : other) : (v < other ? v : other);
     }
   }
+  s_list[tid] = v;
+  __syncthreads();
   if (tid < k) {
     const unsigned long long e = s_list[tid];
     const unsigned idx = 0xffffffffu - (unsigned)(e & 0xffffffffull);
     indices[(long long)blockIdx.x * k + tid] = (long long)idx;
     if (values != nullptr) values[(long long)blockIdx.x * k + tid] = row[idx];
+  }
+}
+
+// ---- the same selection by a thread-block CLUSTER per image ------------------------------------------------
+// One block per image is latency / issue-bound on a single SM (37-41 us for 22,223 scores: 165 k warp instructions
+// on one SM, profiles/r1_aux_passes.md).  Here kTopkCluster blocks (one cluster, 8 SMs) share an image: each stages
+// 1/8 of the keys in its own shared memory and histograms them; the per-block histograms are merged through
+// distributed shared memory (every block reads the eight 256-bin tables and takes the same decision), winners are
+// appended straight into block 0's list over DSMEM, and block 0 sorts them.
+constexpr int kTopkCluster = 8;
+constexpr int kTopkSliceMax = 12288;  // keys per block staged in shared memory (48 KB)
+
+__global__ void __launch_bounds__(kTopkThreads)
+msda_topk_rows_cluster_kernel(const float* __restrict__ scores, long long* __restrict__ indices,
+                              float* __restrict__ values, int row_len, int k) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_merged[256];
+  __shared__ unsigned s_prefix, s_want, s_count_gt, s_eq_count, s_tie_base;
+  __shared__ unsigned s_warp_sum[kTopkThreads / 32];
+  __shared__ unsigned long long s_list[kTopkMax];
+  extern __shared__ unsigned s_keys[];  // this block's slice of the keys (dynamic: up to kTopkSliceMax)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned rank = cluster.block_rank();
+  const int image = blockIdx.x / kTopkCluster;
+  const float* row = scores + (long long)image * row_len;
+  const int slice = (row_len + kTopkCluster - 1) / kTopkCluster;
+  const int lo = (int)rank * slice;
+  const int n_mine = max(0, min(row_len, lo + slice) - lo);
+
+  for (int i = tid; i < n_mine; i += 4 * kTopkThreads) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (i + u * kTopkThreads < n_mine) ? row[lo + i + u * kTopkThreads] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * kTopkThreads < n_mine) s_keys[i + u * kTopkThreads] = topk_key(v[u]);
+  }
+  if (tid == 0) {
+    s_prefix = 0u;
+    s_want = (unsigned)k;
+    s_count_gt = 0u;
+    s_eq_count = 0u;
+    s_tie_base = 0u;
+  }
+  for (int e = tid; e < kTopkMax; e += kTopkThreads) s_list[e] = 0ull;
+  __syncthreads();
+
+  // ---- radix select over the cluster ---------------------------------------------------------------------
+  unsigned prefix_mask = 0u;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (tid < 256) hist[tid] = 0u;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    for (int i0 = 0; i0 < n_mine; i0 += kTopkThreads) {
+      const int i = i0 + tid;
+      unsigned bin = 256u;
+      if (i < n_mine) {
+        const unsigned key = s_keys[i];
+        if ((key & prefix_mask) == prefix) bin = (key >> shift) & 255u;
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (bin < 256u && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+    }
+    cluster.sync();  // all eight tables are complete
+    if (tid < 256) {
+      unsigned sum = 0u;
+#pragma unroll
+      for (int r = 0; r < kTopkCluster; ++r) sum += cluster.map_shared_rank(hist, r)[tid];
+      s_merged[tid] = sum;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      unsigned h[8], mine = 0u;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        h[b] = s_merged[8 * lane + b];
+        mine += h[b];
+      }
+      unsigned suffix = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_down_sync(0xffffffffu, suffix, o);
+        if (lane + o < 32) suffix += t;
+      }
+      const unsigned above = suffix - mine;
+      const unsigned want = s_want;
+      __syncwarp();  // every lane has read s_want before the owning lane rewrites it
+      if (above < want && want <= suffix) {
+        unsigned cum = above, cum_at = 0u;
+        int chosen = -1;
+#pragma unroll
+        for (int b = 7; b >= 0; --b) {
+          if (chosen < 0) {
+            if (want <= cum + h[b]) {
+              chosen = b;
+              cum_at = cum;
+            } else {
+              cum += h[b];
+            }
+          }
+        }
+        s_prefix = prefix | ((unsigned)(8 * lane + chosen) << shift);
+        s_want = want - cum_at;
+      }
+    }
+    prefix_mask |= 255u << shift;
+    cluster.sync();  // every block has read every table (and published its own decision) before the next zero-fill
+  }
+  const unsigned T = s_prefix, ties = s_want, n_gt = (unsigned)k - ties;
+
+  // ---- collection into block 0's list ---------------------------------------------------------------------
+  unsigned long long* list0 = cluster.map_shared_rank(s_list, 0);
+  unsigned* count0 = cluster.map_shared_rank(&s_count_gt, 0);
+  unsigned my_eq = 0u;
+  for (int i0 = 0; i0 < n_mine; i0 += kTopkThreads) {
+    const int i = i0 + tid;
+    unsigned key = 0u;
+    bool gt = false, eq = false;
+    if (i < n_mine) {
+      key = s_keys[i];
+      gt = key > T;
+      eq = key == T;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, gt);
+    if (bal) {
+      unsigned base = 0u;
+      if (lane == 0) base = atomicAdd(count0, (unsigned)__popc(bal));  // one remote atomic per warp
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (gt) list0[base + __popc(bal & ((1u << lane) - 1u))] =
+                  ((unsigned long long)key << 32) | (0xffffffffu - (unsigned)(lo + i));
+    }
+    my_eq += eq ? 1u : 0u;
+  }
+  // ties at the threshold: the first `ties` elements equal to T in index order, i.e. lower ranks first
+#pragma unroll
+  for (int o = 16; o; o >>= 1) my_eq += __shfl_xor_sync(0xffffffffu, my_eq, o);
+  if (lane == 0 && my_eq) atomicAdd(&s_eq_count, my_eq);
+  cluster.sync();
+  unsigned eq_before = 0u;
+  for (unsigned r = 0; r < rank; ++r) eq_before += *cluster.map_shared_rank(&s_eq_count, r);
+  if (s_eq_count != 0u && eq_before < ties) {  // block-uniform
+    for (int i0 = 0; i0 < n_mine; i0 += kTopkThreads) {
+      const int i = i0 + tid;
+      const bool eq = i < n_mine && s_keys[i] == T;
+      const int chunk_ties = __syncthreads_count(eq);
+      if (chunk_ties == 0) continue;
+      const unsigned bal = __ballot_sync(0xffffffffu, eq);
+      if (lane == 0) s_warp_sum[warp] = __popc(bal);
+      __syncthreads();
+      unsigned base = eq_before + s_tie_base;
+      for (int w = 0; w < warp; ++w) base += s_warp_sum[w];
+      if (eq) {
+        const unsigned rnk = base + __popc(bal & ((1u << lane) - 1u));
+        if (rnk < ties) list0[n_gt + rnk] = ((unsigned long long)T << 32) | (0xffffffffu - (unsigned)(lo + i));
+      }
+      __syncthreads();
+      if (tid == 0) s_tie_base += (unsigned)chunk_ties;
+      __syncthreads();
+    }
+  }
+  cluster.sync();  // block 0's list is complete; the other blocks are done
+  if (rank != 0) return;
+
+  unsigned long long v = s_list[tid];
+  for (int size = 2; size <= kTopkMax; size <<= 1) {
+    const bool desc = (tid & size) == 0;
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      unsigned long long other;
+      if (stride >= 32) {
+        s_list[tid] = v;
+        __syncthreads();
+        other = s_list[tid ^ stride];
+        __syncthreads();
+      } else {
+        other = __shfl_xor_sync(0xffffffffu, v, stride);
+      }
+      const bool keep_max = ((tid & stride) == 0) == desc;
+      v = keep_max ? (v > other ? v : other) : (v < other ? v : other);
+    }
+  }
+  if (tid < k) {
+    const unsigned idx = 0xffffffffu - (unsigned)(v & 0xffffffffull);
+    indices[(long long)image * k + tid] = (long long)idx;
+    if (values != nullptr) values[(long long)image * k + tid] = row[idx];
   }
 }
 }  // namespace
@@ -581,7 +815,11 @@ int msda_rowmax_f32(msda_stream_t stream, const float* logits, long long rows, i
     return fail(MSDA_ERR_INVALID_ARGUMENT, "rows=%lld num_classes=%d", rows, num_classes);
   if (rows == 0) return MSDA_OK;
   if (!logits || !scores) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
-  msda_rowmax_kernel<<<aux_grid(rows), kAuxThreads, 0, (cudaStream_t)stream>>>(logits, scores, rows, num_classes);
+  if (num_classes >= 512)
+    msda_rowmax_kernel<32><<<aux_grid(rows), kAuxThreads, 0, (cudaStream_t)stream>>>(logits, scores, rows, num_classes);
+  else
+    msda_rowmax_kernel<8><<<aux_grid((rows + 3) / 4), kAuxThreads, 0, (cudaStream_t)stream>>>(logits, scores, rows,
+                                                                                            num_classes);
   return after_launch("msda_rowmax_kernel");
 }
 
@@ -593,8 +831,45 @@ int msda_topk_rows_f32(msda_stream_t stream, const float* scores, int batch, int
   if (batch == 0) return MSDA_OK;
   if (!scores || !indices) return fail(MSDA_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
   static_assert(sizeof(long long) == sizeof(int64_t), "int64 indices");
-  msda_topk_rows_kernel<<<batch, kTopkThreads, 0, (cudaStream_t)stream>>>(
-      scores, reinterpret_cast<long long*>(indices), values, row_len, k);
+  // default: a cluster of 8 blocks per image (rows of up to 98,304 scores); MSDA_TOPK_NO_CLUSTER=1 or longer rows:
+  // one block per image
+  static const bool no_cluster = getenv("MSDA_TOPK_NO_CLUSTER") && atoi(getenv("MSDA_TOPK_NO_CLUSTER")) != 0;
+  if (!no_cluster && (row_len + kTopkCluster - 1) / kTopkCluster <= kTopkSliceMax) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)batch * kTopkCluster);
+    cfg.blockDim = dim3(kTopkThreads);
+    cfg.dynamicSmemBytes = (size_t)((row_len + kTopkCluster - 1) / kTopkCluster) * sizeof(unsigned);
+    cfg.stream = (cudaStream_t)stream;
+    if (cfg.dynamicSmemBytes > 32 * 1024) {  // static tables take ~10 KB of the 48 KB that need no opt-in
+      const int rc = check_cuda(cudaFuncSetAttribute(msda_topk_rows_cluster_kernel,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     kTopkSliceMax * (int)sizeof(unsigned)),
+                                "shared-memory opt-in of msda_topk_rows_cluster_kernel");
+      if (rc != MSDA_OK) return rc;
+    }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kTopkCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    long long* idx_ll = reinterpret_cast<long long*>(indices);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, msda_topk_rows_cluster_kernel, scores, idx_ll, values, row_len, k);
+    if (e != cudaSuccess) return check_cuda(e, "launch of msda_topk_rows_cluster_kernel");
+    return after_launch("msda_topk_rows_cluster_kernel");
+  }
+  // rows of up to 49,152 scores are staged in shared memory as keys (192 KB); longer rows are re-read from L2
+  const bool staged = row_len <= kTopkStageMax;
+  const size_t dyn = staged ? (size_t)row_len * sizeof(unsigned) : 0;
+  if (dyn > 48 * 1024) {
+    const int rc = check_cuda(cudaFuncSetAttribute(msda_topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   kTopkStageMax * (int)sizeof(unsigned)),
+                              "shared-memory opt-in of msda_topk_rows_kernel");
+    if (rc != MSDA_OK) return rc;
+  }
+  msda_topk_rows_kernel<<<batch, kTopkThreads, dyn, (cudaStream_t)stream>>>(
+      scores, reinterpret_cast<long long*>(indices), values, row_len, k, staged);
   return after_launch("msda_topk_rows_kernel");
 }
 

@@ -314,3 +314,17 @@ def test_topk_proposals_is_the_reference_expression():
         topk_proposals(logits.cuda(), 30000)
     with pytest.raises(RuntimeError, match="at most 1024"):
         topk_proposals(logits.cuda(), 2000)
+
+
+def test_topk_single_block_kernel_matches_the_cluster_kernel():
+    """Rows too long for the cluster's shared-memory slices (> 98,304 scores) take the one-block-per-image kernel;
+    both must agree with torch.topk."""
+    from richsem_b200.ops.functions.aux_functions import topk_rows
+
+    g = torch.Generator().manual_seed(47)
+    for s_len in (98304, 98305, 120000):
+        scores = torch.randn(2, s_len, generator=g)
+        val, idx = topk_rows(scores.cuda(), 300, return_values=True)
+        want_val, _ = torch.topk(scores, 300, dim=1)
+        assert torch.equal(val.cpu(), want_val)
+        assert torch.equal(scores.gather(1, idx.cpu()), want_val)
