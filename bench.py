@@ -64,6 +64,9 @@ def parse_args():
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--lib-flags", type=lambda x: int(x, 0), default=0,
                     help="extra MSDA_FLAG_* bits for forward and backward (kernel-selection experiments)")
+    ap.add_argument("--graph", action="store_true", help="op workloads: capture one step (all forwards + backwards) in a "
+                    "CUDA graph and replay it; matters for decoder-sized calls, whose kernels (14-36 us) are shorter "
+                    "than the Python launch path.  Per-launch times are then not available: the roofline is the step's")
     ap.add_argument("--eager", action="store_true", help="encoder_stack6: no CUDA graph")
     ap.add_argument("--fuse-prologue", action="store_true", help="encoder_stack6: fused softmax + "
                     "sampling-location prologue (SURVEY 8f-1)")
@@ -278,6 +281,20 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
+    launches_per_step = None
+    if args.graph:
+        l0 = _capi.launch_count()
+        step()
+        launches_per_step = _capi.launch_count() - l0
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        eager_step = step
+        step = lambda timing=None: graph.replay()
+        for _ in range(3):
+            step()
+        sync_all()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     timings = [{k: [ev() for _ in range(layers)] for k in ("f0", "f1", "b0", "b1")} for _ in range(args.steps)]
@@ -290,21 +307,29 @@ def run_b200(args):
     sync_all()
     start.record()
     for k in range(args.steps):
-        step(timings[k])
+        step(None if args.graph else timings[k])
     stop.record()
     sync_all()
-    launches = _capi.launch_count() - launches0
+    launches = _capi.launch_count() - launches0 if not args.graph else launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = max_over_ranks(start.elapsed_time(stop), world, dev) / args.steps
     value = aggregate_qps(queries_per_step, world, ms_per_step)
 
-    fwd_ms = statistics.mean(tm["f0"][i].elapsed_time(tm["f1"][i]) for tm in timings for i in range(layers))
-    bwd_ms = statistics.mean(tm["b0"][i].elapsed_time(tm["b1"][i]) for tm in timings for i in range(layers))
+    if args.graph:
+        # no events inside a replayed graph: split the step in the ratio of the algorithmic bytes (reported as such)
+        per_layer = ms_per_step / layers
+        fwd_ms = per_layer * fwd_bytes / (fwd_bytes + bwd_bytes)
+        bwd_ms = per_layer - fwd_ms
+    else:
+        fwd_ms = statistics.mean(tm["f0"][i].elapsed_time(tm["f1"][i]) for tm in timings for i in range(layers))
+        bwd_ms = statistics.mean(tm["b0"][i].elapsed_time(tm["b1"][i]) for tm in timings for i in range(layers))
     peak, peak_src = peaks()
 
     # ---- e2e: the same step through the public API with HOST buffers ------------------------
     e2e = None
     if not args.no_e2e:
+        if args.graph:
+            step = eager_step
         e2e = run_e2e(args, torch, dist, ext, sets, shp, st, flags, world, dev, queries_per_step)
 
     if rank != 0:
@@ -334,6 +359,8 @@ def run_b200(args):
                    "batch_per_gpu": bs, "layers_per_step": layers, "heads": 8, "head_dim": 32, "points": 4,
                    "locations": kind, "grad_value_mode": "deterministic" if args.deterministic else "atomic (merged on chip per window cell, then fp32 L2 reductions)",
                    "parallelism": f"batch-sharded x{world}, no collective in the op",
+                   "launch": "one CUDA graph per step, replayed (per-launch times not measured: fwd / bwd split by "
+                             "algorithmic bytes)" if args.graph else "eager, one library call per layer and direction",
                    "l2_policy": f"{layers} distinct input sets per step ({in_bytes / 1e6:.0f} MB of inputs) "
                                 "larger than the 126 MB L2; no explicit flush"},
         "roofline": {"bound": "hbm", "kernel": f"msda {dom} ({'memset + ' if dom == 'backward' else ''}kernel), avg of "
