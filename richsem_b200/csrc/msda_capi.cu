@@ -90,6 +90,7 @@ int make_problem(cudaStream_t stream, const int64_t* shapes, const int64_t* star
                 opts->struct_size, sizeof(msda_opts));
   pb->d = MsdaDims{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   pb->fz = MsdaFused{nullptr, 0};
+  pb->pdl_after_fill = false;
   pb->flags = opt_flags(opts);
   pb->order = opts ? opts->query_order : nullptr;
   pb->order_len = pb->order ? opts->query_order_len : num_query;
@@ -158,7 +159,21 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
   const size_t gv_bytes = (size_t)batch * spatial_size * num_heads * channels * sizeof(TA);
   // deterministic mode writes every grad_value row itself
   if (!(pb.flags & MSDA_FLAG_GRAD_VALUE_PREZEROED) && !(det && num_query > 0) && !no_gv) {
-    rc = check_cuda(cudaMemsetAsync(gv, 0, gv_bytes, s), "zero-fill of grad_value");
+    // decoder-sized fp32-gradient problems (split kernel): the fill is a third of the backward's time, so it is a kernel
+    // of this library that the backward kernel overlaps with its gather phase (programmatic dependent launch)
+    bool pdl = false;
+    if constexpr (sizeof(TA) == 4) {
+      static const bool no_pdl = getenv("MSDA_B200_NO_PDL") && atoi(getenv("MSDA_B200_NO_PDL")) != 0;
+      pdl = !no_pdl && num_query > 0 && !det && !(pb.flags & MSDA_FLAG_FORCE_GENERIC) &&
+            fast_shape(sizeof(TV), channels, num_levels, num_point) && fits_int32(pb.d) && msda::use_split(pb) &&
+            aligned(gv, 16) && gv_bytes % 16 == 0;
+    }
+    if (pdl) {
+      rc = msda::zero_fill_pdl(s, reinterpret_cast<float*>(gv), gv_bytes);
+      pb.pdl_after_fill = true;
+    } else {
+      rc = check_cuda(cudaMemsetAsync(gv, 0, gv_bytes, s), "zero-fill of grad_value");
+    }
     if (rc != MSDA_OK) return rc;
   }
   if (num_query == 0) return MSDA_OK;

@@ -648,13 +648,6 @@ msda_bwd_d32_split_kernel(const VT* __restrict__ grad_out, const VT* __restrict_
           const ptrdiff_t o = ((k & 2) ? o2 : o0) + ((k & 1) ? M32 : 0);
           float v[C];
           RT::load(value_b + o, v);
-          if (kScatter) {
-            const float t = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
-#pragma unroll
-            for (int i2 = 0; i2 < SD::N; ++i2)
-              red_add_f4(gvalue_img + o + SD::offset(j, i2), t * gs[4 * i2], t * gs[4 * i2 + 1], t * gs[4 * i2 + 2],
-                         t * gs[4 * i2 + 3]);
-          }
           float sdot = 0.f;
 #pragma unroll
           for (int c = 0; c < C; ++c) sdot = fmaf(go[c], v[c], sdot);
@@ -674,6 +667,36 @@ msda_bwd_d32_split_kernel(const VT* __restrict__ grad_out, const VT* __restrict_
     if (j == 0 && p < LP) {
       st_stream_f2(grad_loc + (qm * LP + p) * 2, make_float2(gx, gy));
       st_stream_f1(grad_attw + qm * LP + p, ga);
+    }
+  }
+  if (kScatter) {
+    // the scatter needs no value rows, only the records and grad_out: it runs after the gather phase, behind the
+    // completion of the preceding kernel on the stream (the zero-fill of grad_value when the launch allowed an early
+    // start; otherwise the wait returns at once)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < NPG; ++i) {
+      const int p = g + GPW * i;
+      if (p < LP) {
+        const int l = p / kP;
+        const float4 r = rec[p];
+        const int bm = __float_as_int(r.x);
+        const float lh = r.y, lw = r.z, a = r.w;
+        const float a_hh = a * (1.f - lh), a_lh = a * lh, hw = 1.f - lw;
+        const ptrdiff_t o0 = (ptrdiff_t)(bm & ~31);
+        const ptrdiff_t o2 = o0 + (ptrdiff_t)(lv.W[l] * M32);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (bm & (1 << k)) {
+            const ptrdiff_t o = ((k & 2) ? o2 : o0) + ((k & 1) ? M32 : 0);
+            const float t = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
+#pragma unroll
+            for (int i2 = 0; i2 < SD::N; ++i2)
+              red_add_f4(gvalue_img + o + SD::offset(j, i2), t * gs[4 * i2], t * gs[4 * i2 + 1], t * gs[4 * i2 + 2],
+                         t * gs[4 * i2 + 3]);
+          }
+        }
+      }
     }
   }
 }

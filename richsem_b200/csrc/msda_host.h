@@ -25,6 +25,9 @@ struct Problem {
   int order_len;
   uint32_t flags;
   MsdaFused fz;  // ref_dim 0: the reference op; 2 | 4: fused prologue (loc / attw are the raw Linear outputs)
+  // the library's own zero-fill kernel of grad_value is the launch right before the backward kernel on this stream: the
+  // backward may start early (programmatic dependent launch) and waits (griddepcontrol.wait) before its first reduction
+  bool pdl_after_fill;
 };
 
 // Few (query, head) pairs (decoder cross-attention): one warp per pair instead of one lane group.
@@ -33,6 +36,9 @@ inline bool use_split(const Problem& pb) {
          (long long)pb.d.batch * pb.d.num_query * pb.d.num_heads <= 65536 && pb.d.num_levels >= 2 &&
          pb.d.num_levels <= 6;
 }
+
+// Zero-fill of grad_value as a kernel (16-byte stores) that lets the next kernel on the stream launch early.
+int zero_fill_pdl(cudaStream_t s, float* p, size_t bytes);
 
 // ---- head_dim 32, 4 points, 1..6 levels; VT = float | __nv_bfloat16 (explicitly instantiated) ----
 // msda_launch_d32.cu: L1-gather kernels (tiled for large problems, split for small ones).

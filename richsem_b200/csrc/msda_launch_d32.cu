@@ -55,10 +55,29 @@ int launch_bwd_split(cudaStream_t s, const Problem& pb, const VT* grad_out, cons
                      const float* loc, const float* attw, float* gv, float* gl, float* ga) {
   constexpr int QPB = msda::kSplitThreads / 32;
   dim3 grid(((pb.d.num_query + QPB - 1) / QPB) * pb.d.num_heads, pb.d.batch);
+  if (kScatter && pb.pdl_after_fill) {
+    // programmatic dependent launch behind msda_zero_fill_kernel (see zero_fill_pdl)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(msda::kSplitThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, msda::msda_bwd_d32_split_kernel<VT, kL, 4, kM, kScatter>, grad_out, value,
+                                             loc, attw, gv, gl, ga, pb.lv, pb.d.spatial_size, pb.d.num_heads,
+                                             pb.d.num_query);
+    if (e != cudaSuccess) return check_cuda(e, "launch of msda_bwd_d32_split_kernel");
+    return after_launch("msda_bwd_d32_split_kernel");
+  }
   msda::msda_bwd_d32_split_kernel<VT, kL, 4, kM, kScatter><<<grid, msda::kSplitThreads, 0, s>>>(
       grad_out, value, loc, attw, gv, gl, ga, pb.lv, pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
   return after_launch("msda_bwd_d32_split_kernel");
 }
+
 
 #define MSDA_SWITCH_L(L_, CALL)                                                              \
   switch (L_) {                                                                              \
@@ -131,5 +150,27 @@ INST_BWD(float, false)
 INST_BWD(__nv_bfloat16, true)
 INST_BWD(__nv_bfloat16, false)
 #undef INST_BWD
+
+namespace {
+// Zero-fill of grad_value.  `griddepcontrol.launch_dependents` right away: the backward kernel launched behind it
+// with the programmatic-serialization attribute may become resident as soon as every block of this grid has started,
+// and runs its decode / gather / dot-product phase while the fill is still writing.
+__global__ void __launch_bounds__(256) msda_zero_fill_kernel(float4* __restrict__ p, const size_t n16) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += (size_t)gridDim.x * 256) p[i] = z;
+}
+}  // namespace
+
+int zero_fill_pdl(cudaStream_t s, float* p, size_t bytes) {
+  const size_t n16 = bytes / 16;
+  // many short-lived blocks (not a persistent grid): SM slots free up while the fill is still running, so that the
+  // dependent backward kernel's blocks can move in next to it
+  size_t blocks = (n16 + 256 * 16 - 1) / (256 * 16);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  msda_zero_fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<float4*>(p), n16);
+  return after_launch("msda_zero_fill_kernel");
+}
 
 }  // namespace msda
