@@ -211,8 +211,11 @@ __device__ __forceinline__ void d32_decode_points(const float* __restrict__ loc,
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
+#ifndef MSDA_FWD_MINBLOCKS
+#define MSDA_FWD_MINBLOCKS 1
+#endif
 template <typename VT, int kL, int kP, int kM>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MSDA_FWD_MINBLOCKS)
 msda_fwd_d32_kernel(const VT* __restrict__ value, const float* __restrict__ loc,
                     const float* __restrict__ attw, VT* __restrict__ out,
                     const int* __restrict__ order, const int order_len,
