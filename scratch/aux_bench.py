@@ -93,10 +93,7 @@ def main():
     tms = timeit([lambda x=x: x.masked_fill(mask[..., None], 0.0) for x in xs], a.iters)
     report("zero_masked_rows_f32", ms, alg, tms, "vs out-of-place masked_fill")
     # 8f-4: read memory (kept rows) + mask, write memory + proposals
-    sys.path.insert(0, str(ROOT))
-    from oracle.aux_oracle import encoder_proposals  # checker only: which rows are kept
-
-    keep = int(torch.isfinite(encoder_proposals(torch.zeros(n, S, 4), mask.cpu(), shapes)[1][..., 0]).sum())
+    keep = int(torch.isfinite(gen_encoder_output_proposals(xs[0], mask, shp)[1][..., 0]).sum())  # rows that are read
     alg = keep * c * 4 + rows + rows * c * 4 + rows * 16
     ms = timeit([lambda x=x: gen_encoder_output_proposals(x, mask, shp) for x in xs], a.iters)
 

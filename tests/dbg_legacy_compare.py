@@ -1,3 +1,5 @@
+"""Debug helper (not a test): this library, the C oracle and the reference CUDA kernels (oracle/_ref) side by side on one
+encoder layer.  Lives under tests/ because only tests may use oracle/.   python tests/dbg_legacy_compare.py"""
 import sys; sys.path.insert(0, ".")
 import torch
 from oracle.msda_oracle import LegacyCuda, COracle
