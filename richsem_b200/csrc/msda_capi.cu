@@ -164,9 +164,13 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
     bool pdl = false;
     if constexpr (sizeof(TA) == 4) {
       static const bool no_pdl = getenv("MSDA_B200_NO_PDL") && atoi(getenv("MSDA_B200_NO_PDL")) != 0;
+      // ... and the window kernel of encoder-sized problems, whose whole front end precedes its first reduction
+      const bool split = msda::use_split(pb);
+      const bool window = !split && !(pb.flags & (MSDA_FLAG_NO_WINDOW | MSDA_FLAG_BWD_HALVES | MSDA_FLAG_BWD_WS));
       pdl = !no_pdl && num_query > 0 && !det && !(pb.flags & MSDA_FLAG_FORCE_GENERIC) &&
-            fast_shape(sizeof(TV), channels, num_levels, num_point) && fits_int32(pb.d) && msda::use_split(pb) &&
-            aligned(gv, 16) && gv_bytes % 16 == 0;
+            fast_shape(sizeof(TV), channels, num_levels, num_point) && fits_int32(pb.d) && (split || window) &&
+            aligned(value, 16) && aligned(gv, 16) && aligned(loc, 16) && aligned(attw, 16) && aligned(grad_out, 16) &&
+            aligned(gl, 16) && aligned(ga, 16) && gv_bytes % 16 == 0;
     }
     if (pdl) {
       rc = msda::zero_fill_pdl(s, reinterpret_cast<float*>(gv), gv_bytes);

@@ -1148,6 +1148,10 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
   if (kM) a.M = kM;
   const int m = blockIdx.x % a.M, tile = blockIdx.x / a.M, b = blockIdx.y;
   win_bwd_produce<VT, kL, kWinPool, kDet, kFused>(sm, a, lv, tile, m, b, (int)threadIdx.x, BlockSync{});
+  // the front end writes nothing to global memory; everything from here on may reduce into grad_value, which the
+  // preceding kernel on the stream zero-fills when this kernel was allowed to start early (programmatic dependent
+  // launch, msda_capi.cu); otherwise the wait returns at once
+  if (!kDet) asm volatile("griddepcontrol.wait;" ::: "memory");
   win_bwd_consume<VT, kL, kWinPool, kDet, kFused>(sm, a, lv, tile, m, b, (int)threadIdx.x, BlockSync{});
 }
 

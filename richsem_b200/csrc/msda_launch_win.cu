@@ -62,6 +62,22 @@ int launch_bwd_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* va
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
   WinBwdArgs a = make_bwd_args(pb, go, value, loc, attw, gv, gl, ga);
   a.gv64 = gv64; a.maxbits = maxbits;
+  if (!kDet && pb.pdl_after_fill) {
+    // programmatic dependent launch behind msda_zero_fill_kernel: the front end overlaps the fill
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kWinThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, pb.lv);
+    if (e != cudaSuccess) return check_cuda(e, "launch of msda_bwd_d32_win_kernel");
+    return after_launch("msda_bwd_d32_win_kernel");
+  }
   kern<<<grid, kWinThreads, kSmem, s>>>(a, pb.lv);
   return after_launch("msda_bwd_d32_win_kernel");
 }
