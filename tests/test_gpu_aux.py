@@ -328,3 +328,42 @@ def test_topk_single_block_kernel_matches_the_cluster_kernel():
         want_val, _ = torch.topk(scores, 300, dim=1)
         assert torch.equal(val.cpu(), want_val)
         assert torch.equal(scores.gather(1, idx.cpu()), want_val)
+
+
+# ---- randomized sweeps (seeded) over shapes the fixed cases do not hit ---------------------------------------
+def test_randomized_proposals_and_selection_sweep():
+    """30 random pyramids (1-5 levels, odd sizes, channel counts that are any multiple of 4), random rectangular or
+    scattered padding, random k: proposals against the oracle, selection against torch."""
+    import random
+
+    from richsem_b200.ops.functions import topk_proposals
+
+    rnd = random.Random(2024)
+    for it in range(30):
+        levels = rnd.randint(1, 5)
+        shapes = [(rnd.randint(1, 40), rnd.randint(1, 40)) for _ in range(levels)]
+        s = sum(h * w for h, w in shapes)
+        n = rnd.randint(1, 4)
+        c = 4 * rnd.randint(1, 70)
+        g = torch.Generator().manual_seed(1000 + it)
+        memory = torch.randn(n, s, c, generator=g)
+        kind = rnd.choice(["none", "rect", "scattered"])
+        if kind == "none":
+            mask = None
+        elif kind == "rect":
+            mask = torch.stack([_rect(shapes, (rnd.uniform(0.05, 1.0), rnd.uniform(0.05, 1.0))) for _ in range(n)])
+        else:
+            mask = torch.rand(n, s, generator=g) < rnd.uniform(0.0, 0.9)
+        wh = None if rnd.random() < 0.7 else torch.tensor([rnd.uniform(-3, 1), rnd.uniform(-3, 1)])
+        _check_proposals(memory, mask, shapes, wh)
+        kc = rnd.choice([1, 3, 17, 91, 130, 515, 1203])
+        logits = torch.randn(n, s, kc, generator=g)
+        if rnd.random() < 0.3:  # a few masked-looking rows: identical logits
+            logits[:, : s // 3] = -1.5
+        k = rnd.randint(1, min(s, 1024))
+        got = topk_proposals(logits.cuda(), k).cpu()
+        sc = logits.max(-1)[0]
+        want_val = torch.topk(sc, k, dim=1)[0]
+        assert torch.equal(sc.gather(1, got), want_val), (it, shapes, kc, k)
+        for b in range(n):
+            assert len(set(got[b].tolist())) == k
