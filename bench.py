@@ -363,7 +363,7 @@ def run_b200(args):
                              "algorithmic bytes)" if args.graph else "eager, one library call per layer and direction",
                    "l2_policy": f"{layers} distinct input sets per step ({in_bytes / 1e6:.0f} MB of inputs) "
                                 "larger than the 126 MB L2; no explicit flush"},
-        "roofline": {"bound": "hbm", "kernel": f"msda {dom} ({'memset + ' if dom == 'backward' else ''}kernel), avg of "
+        "roofline": {"bound": "hbm", "kernel": f"msda {dom} ({'zero-fill of grad_value + ' if dom == 'backward' else ''}kernel), avg of "
                      f"{args.steps * layers} launches", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
                      "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms},
