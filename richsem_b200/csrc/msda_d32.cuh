@@ -603,8 +603,14 @@ msda_fwd_d32_split_kernel(const VT* __restrict__ value, const float* __restrict_
   if (g == 0) RT::store_stream(out + qm * 32 + j * C, acc);
 }
 
+// Resident blocks per SM (of 128 threads) the split backward is compiled for.  Measured on the graph-replayed decoder step
+// (6 layers): fp32 value 1 -> 0.3185 ms, 12 (40 registers) -> 0.3115 ms, 16 (32 registers, spills) -> 0.3194 ms; bf16 value
+// 1 (54 registers) -> 0.2931 ms, 12 -> 0.3079 ms, 16 -> 0.3427 ms.  Hence 12 for fp32 and ptxas's own choice (no minimum) for bf16.
+#ifndef MSDA_SPLIT_BWD_MINBLOCKS
+#define MSDA_SPLIT_BWD_MINBLOCKS(VT) (sizeof(VT) == 4 ? 12 : 0)  // 0 = no minimum
+#endif
 template <typename VT, int kL, int kP, int kM, bool kScatter>
-__global__ void __launch_bounds__(kSplitThreads)
+__global__ void __launch_bounds__(kSplitThreads, MSDA_SPLIT_BWD_MINBLOCKS(VT))
 msda_bwd_d32_split_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                           const float* __restrict__ loc, const float* __restrict__ attw,
                           float* __restrict__ grad_value, float* __restrict__ grad_loc,
