@@ -327,9 +327,7 @@ def run_b200(args):
 
     # ---- e2e: the same step through the public API with HOST buffers ------------------------
     e2e = None
-    if not args.no_e2e:
-        if args.graph:
-            step = eager_step
+    if not args.no_e2e and not args.graph:  # e2e is measured on the eager path (the public call with host buffers)
         e2e = run_e2e(args, torch, dist, ext, sets, shp, st, flags, world, dev, queries_per_step)
 
     if rank != 0:
