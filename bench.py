@@ -75,6 +75,7 @@ def parse_args():
     ap.add_argument("--padding", action="store_true", help="encoder_stack6: image 1 of each pair is padded (mask path)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the additional workloads / comparator legs of the default line")
     ap.add_argument("--e2e-steps", type=int, default=12)
     return ap.parse_args()
 

@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 2
+#define MSDA_ABI_VERSION 3
 #define MSDA_MAX_LEVELS 16
 
 /* status codes */
@@ -66,16 +66,18 @@ extern "C" {
 #define MSDA_FLAG_DETERMINISTIC 0x1u          /* bitwise reproducible grad_value (fixed-point accumulation of canonically
                                                  ordered partial sums, or sort-by-corner segmented sums); needs workspace */
 #define MSDA_FLAG_GRAD_VALUE_PREZEROED 0x2u   /* caller already zeroed grad_value (or wants accumulation)           */
-#define MSDA_FLAG_FORCE_GENERIC 0x4u          /* bypass the D=32 fast kernels (testing)                             */
-#define MSDA_FLAG_COORDS_FMA 0x10u             /* pixel coordinate = fma(loc, size, -0.5): what nvcc -fmad=true makes of
+#define MSDA_FLAG_FORCE_GENERIC 0x4u          /* bypass the head_dim-32 kernels (testing)                           */
+#define MSDA_FLAG_COORDS_FMA 0x10u            /* pixel coordinate = fma(loc, size, -0.5): what nvcc -fmad=true makes of
                                                  cuh:285-286, i.e. the compiled reference; default is mul-then-sub  */
-#define MSDA_FLAG_NO_WINDOW 0x80u              /* backward: keep the L1-gather tiled kernel instead of the shared-memory window kernel */
-#define MSDA_FLAG_BWD_WS 0x1000u               /* backward: persistent warp-specialised window kernel (producer / consumer groups) */
-#define MSDA_FLAG_BWD_HALVES 0x800u            /* backward: gather kernel + cell-sorted grad_value kernel instead of the fused window kernel */
-#define MSDA_FLAG_NO_GRAD_VALUE 0x400u         /* backward: value needs no gradient; grad_value is not touched and may be NULL   */
-#define MSDA_FLAG_LDG256 0x200u                /* forward, fp32: 256-bit gathers, 4 lanes per (query, head) (opt-in, comparison)  */
-#define MSDA_FLAG_WINDOW_FWD 0x100u            /* forward: use the shared-memory window kernel (opt-in, slower on B200)        */
-#define MSDA_FLAG_NO_SPLIT 0x8u               /* small problems: keep the lane-group-per-query kernels (testing)    */
+#define MSDA_FLAG_NO_GRAD_VALUE 0x400u        /* backward: value needs no gradient; grad_value is not touched and may be NULL */
+
+/* msda_opts.kernel_hint: which kernel family serves a head_dim-32 problem.  0 lets the library decide (split for
+ * at most 65,536 (query, head) pairs, else window when a query order is given, else tiled); the other values
+ * exist so that tests and tuning runs can put a small problem through the large-problem kernels. */
+#define MSDA_KERNEL_AUTO 0
+#define MSDA_KERNEL_SPLIT 1  /* one warp per (query, head): decoder-sized problems                                  */
+#define MSDA_KERNEL_TILED 2  /* one lane group per (query, head), L1 gather, one L2 reduction per sampled corner    */
+#define MSDA_KERNEL_WINDOW 3 /* backward: shared-memory window, cell-sorted on-chip merging (forward: tiled)        */
 
 typedef void* msda_stream_t; /* cudaStream_t */
 
@@ -90,7 +92,7 @@ typedef struct msda_opts {
    * locality, never results.  NULL = natural order. */
   const int32_t* query_order;
   int32_t query_order_len;
-  int32_t reserved0;
+  int32_t kernel_hint;                    /* MSDA_KERNEL_*; 0 = automatic */
   void* workspace;                        /* DEVICE scratch for MSDA_FLAG_DETERMINISTIC */
   size_t workspace_bytes;
 } msda_opts;

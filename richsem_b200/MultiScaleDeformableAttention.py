@@ -118,7 +118,7 @@ class _on_device:
 
 
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step,
-                           _flags: int = 0):
+                           _flags: int = 0, _kernel: int = 0):
     _check_inputs((("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                    ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)))
     n, s, m, d, nl, lq, npt = _dims(value, spatial_shapes, sampling_loc, attn_weight, im2col_step)
@@ -127,7 +127,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     out = torch.empty((n, lq, m * d), dtype=value.dtype, device=value.device)
     if out.numel() == 0:
         return out
-    opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=_flags)
+    opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=_flags, kernel=_kernel)
     with _on_device(value.device):
         rc = _FWD[sfx](
             _stream(value.device), value.data_ptr(), _dev_ptr(spatial_shapes), _dev_ptr(level_start_index),
@@ -146,7 +146,7 @@ def _workspace(nbytes, device):
 
 
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-                            im2col_step, _flags: int = 0, _need_grad_value: bool = True):
+                            im2col_step, _flags: int = 0, _need_grad_value: bool = True, _kernel: int = 0):
     """Same arguments and return value as the reference's binding (vision.cpp:15).  `_need_grad_value=False`
     (an addition; the autograd Function passes `ctx.needs_input_grad[0]`) skips the grad_value scatter — the
     more expensive half of the backward — and returns None in its place."""
@@ -171,7 +171,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
         flags |= _capi.FLAG_DETERMINISTIC
     if flags & _capi.FLAG_DETERMINISTIC:
         ws = _workspace(_capi.lib.msda_backward_workspace_bytes(n, s, m, d, nl, lq, npt), value.device)
-    opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=flags, workspace=ws)
+    opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=flags, workspace=ws, kernel=_kernel)
     with _on_device(value.device):
         rc = _BWD[sfx](
             _stream(value.device), grad_output.data_ptr(), value.data_ptr(), _dev_ptr(spatial_shapes),
@@ -191,9 +191,9 @@ _BWD_FUSED = {k: getattr(_capi.lib, "msda_backward_fused_" + k) for k in ("f32",
 
 def fused_prologue_supported(value, num_levels, num_query, num_point) -> bool:
     """True when the library has fused-prologue kernels for this problem: CUDA fp32 / bf16 value, head_dim 32,
-    4 points, at most 6 levels, more than 65,536 (query, head) pairs, default (non-deterministic) mode."""
+    4 points, 3 to 5 levels, more than 65,536 (query, head) pairs, default (non-deterministic) mode."""
     return (value.is_cuda and value.dtype in (torch.float32, torch.bfloat16) and value.dim() == 4 and value.shape[3] == 32
-            and num_point == 4 and 1 <= num_levels <= 6 and value.shape[0] * num_query * value.shape[2] > 65536
+            and num_point == 4 and 3 <= num_levels <= 5 and value.shape[0] * num_query * value.shape[2] > 65536
             and not is_deterministic())
 
 
@@ -213,14 +213,14 @@ def _fused_args(value, spatial_shapes, level_start_index, reference_points, samp
 
 
 def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
-                                 attn_logits, im2col_step, _flags: int = 0):
+                                 attn_logits, im2col_step, _flags: int = 0, _kernel: int = 0):
     """out (N, Lq, M*D) from the RAW sampling offsets (N, Lq, M, L, P, 2) and attention logits (N, Lq, M, L*P)."""
     (n, s, m, d, nl, lq, npt), ref_dim = _fused_args(value, spatial_shapes, level_start_index, reference_points,
                                                      sampling_offsets, attn_logits, im2col_step)
     sfx = _SUFFIX[value.dtype]
     meta = _capi.level_meta(spatial_shapes, level_start_index)
     out = torch.empty((n, lq, m * d), dtype=value.dtype, device=value.device)
-    opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=_flags)
+    opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=_flags, kernel=_kernel)
     with _on_device(value.device):
         rc = _FWD_FUSED[sfx](
             _stream(value.device), value.data_ptr(), _dev_ptr(spatial_shapes), _dev_ptr(level_start_index),
@@ -231,7 +231,7 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
 
 
 def ms_deform_attn_backward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
-                                  attn_logits, grad_output, im2col_step, _flags: int = 0):
+                                  attn_logits, grad_output, im2col_step, _flags: int = 0, _kernel: int = 0):
     """[grad_value, grad_sampling_offsets, grad_attn_logits]; no gradient for reference_points."""
     (n, s, m, d, nl, lq, npt), ref_dim = _fused_args(value, spatial_shapes, level_start_index, reference_points,
                                                      sampling_offsets, attn_logits, im2col_step)
@@ -242,7 +242,7 @@ def ms_deform_attn_backward_fused(value, spatial_shapes, level_start_index, refe
     grad_value = torch.empty(value.shape, dtype=torch.float32, device=value.device)  # zero-filled by the library
     grad_offsets = torch.empty_like(sampling_offsets)
     grad_logits = torch.empty_like(attn_logits)
-    opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=_flags)
+    opts = _capi.make_opts(meta, order=_capi.query_order(meta, lq, value.device), flags=_flags, kernel=_kernel)
     with _on_device(value.device):
         rc = _BWD_FUSED[sfx](
             _stream(value.device), grad_output.data_ptr(), value.data_ptr(), _dev_ptr(spatial_shapes),

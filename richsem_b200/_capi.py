@@ -18,18 +18,14 @@ _LIB_PATH = Path(os.environ.get("MSDA_B200_LIB") or Path(__file__).resolve().par
 
 MSDA_OK = 0
 MSDA_ERR_UNSUPPORTED = 2
-MSDA_ABI_VERSION = 2
+MSDA_ABI_VERSION = 3
 FLAG_DETERMINISTIC = 0x1
 FLAG_GRAD_VALUE_PREZEROED = 0x2
 FLAG_FORCE_GENERIC = 0x4
-FLAG_NO_SPLIT = 0x8
 FLAG_COORDS_FMA = 0x10
-FLAG_NO_WINDOW = 0x80
-FLAG_WINDOW_FWD = 0x100
-FLAG_LDG256 = 0x200
 FLAG_NO_GRAD_VALUE = 0x400
-FLAG_BWD_HALVES = 0x800
-FLAG_BWD_WS = 0x1000
+# msda_opts.kernel_hint (testing / tuning: which kernel family serves a head_dim-32 problem; 0 = the library decides)
+KERNEL_AUTO, KERNEL_SPLIT, KERNEL_TILED, KERNEL_WINDOW = 0, 1, 2, 3
 MAX_LEVELS = 16
 
 _vp, _i, _i64p = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)
@@ -45,7 +41,7 @@ class MsdaOpts(ctypes.Structure):
         ("level_start_index_host", _i64p),
         ("query_order", _vp),
         ("query_order_len", ctypes.c_int32),
-        ("reserved0", ctypes.c_int32),
+        ("kernel_hint", ctypes.c_int32),
         ("workspace", _vp),
         ("workspace_bytes", ctypes.c_size_t),
     ]
@@ -145,7 +141,9 @@ _meta_lock = threading.Lock()
 
 
 def _tensor_key(t: torch.Tensor):
-    return (id(t), t._version)
+    # inference tensors (created under torch.inference_mode) do not track a version counter and cannot be
+    # modified in place outside inference mode: identity alone keys them
+    return (id(t), -1 if t.is_inference() else t._version)
 
 
 def level_meta(spatial_shapes: torch.Tensor, level_start_index: torch.Tensor) -> LevelMeta:
@@ -234,26 +232,27 @@ def query_order(meta: LevelMeta, num_query: int, device) -> "torch.Tensor | None
 _opts_cache: dict = {}
 
 
-def make_opts(meta: LevelMeta, order=None, flags=0, workspace=None) -> MsdaOpts:
+def make_opts(meta: LevelMeta, order=None, flags=0, workspace=None, kernel=KERNEL_AUTO) -> MsdaOpts:
     """msda_opts for a launch.  Structs are immutable once built, so they are cached per
-    (level table, order buffer, flags, workspace) to keep the per-call host cost down."""
+    (level table, order buffer, flags, workspace, kernel hint) to keep the per-call host cost down."""
     key = (id(meta), order.data_ptr() if order is not None else 0, flags,
            workspace.data_ptr() if workspace is not None else 0,
-           workspace.numel() if workspace is not None else 0)
+           workspace.numel() if workspace is not None else 0, kernel)
     hit = _opts_cache.get(key)
     if hit is not None and hit[1] is meta:
         return hit[0]
-    o = _build_opts(meta, order, flags, workspace)
+    o = _build_opts(meta, order, flags, workspace, kernel)
     if len(_opts_cache) > 512:
         _opts_cache.clear()
     _opts_cache[key] = (o, meta, order, workspace)  # keep the referenced buffers alive
     return o
 
 
-def _build_opts(meta, order, flags, workspace) -> MsdaOpts:
+def _build_opts(meta, order, flags, workspace, kernel=KERNEL_AUTO) -> MsdaOpts:
     o = MsdaOpts()
     o.struct_size = ctypes.sizeof(MsdaOpts)
     o.flags = flags
+    o.kernel_hint = kernel
     o.spatial_shapes_host = ctypes.cast(meta.c_shapes, _i64p)
     o.level_start_index_host = ctypes.cast(meta.c_starts, _i64p)
     if order is not None:

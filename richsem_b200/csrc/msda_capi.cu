@@ -92,6 +92,9 @@ int make_problem(cudaStream_t stream, const int64_t* shapes, const int64_t* star
   pb->fz = MsdaFused{nullptr, 0};
   pb->pdl_after_fill = false;
   pb->flags = opt_flags(opts);
+  pb->kernel_hint = opts ? opts->kernel_hint : MSDA_KERNEL_AUTO;
+  if (pb->kernel_hint < MSDA_KERNEL_AUTO || pb->kernel_hint > MSDA_KERNEL_WINDOW)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_opts.kernel_hint=%d is not one of MSDA_KERNEL_*", pb->kernel_hint);
   pb->order = opts ? opts->query_order : nullptr;
   pb->order_len = pb->order ? opts->query_order_len : num_query;
   if (pb->order && pb->order_len < num_query)
@@ -106,7 +109,7 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 
 bool fast_shape(int dtype_bytes, int channels, int num_levels, int num_point) {
   return (dtype_bytes == 4 || dtype_bytes == 2) && channels == 32 && num_point == 4 &&
-         num_levels >= 1 && num_levels <= 6;
+         num_levels >= 3 && num_levels <= 5;  // DINO-family pyramids; anything else takes the generic kernels
 }
 
 bool fits_int32(const MsdaDims& d) {
@@ -130,11 +133,7 @@ int forward_impl(cudaStream_t s, const TV* value, const int64_t* shapes, const i
     if (!(pb.flags & MSDA_FLAG_FORCE_GENERIC) && fast_shape(sizeof(TV), channels, num_levels, num_point) &&
         fits_int32(pb.d) && aligned(value, 16) && aligned(loc, 16) && aligned(attw, 16) && aligned(out, 16))
     {
-      // measured on B200 (profiles/): the shared-memory window forward is latency-bound behind its front end
-      // (0.18 ms per bs=2 encoder layer against 0.14 ms for the L1-gather kernel), so it is opt-in; the window
-      // backward is the default for large problems (0.41 ms against 0.47 ms)
-      const bool window = !msda::use_split(pb) && (pb.flags & MSDA_FLAG_WINDOW_FWD) && !(pb.flags & MSDA_FLAG_NO_WINDOW);
-      return window ? msda::fwd_d32_win<TV>(s, pb, value, loc, attw, out) : msda::fwd_d32<TV>(s, pb, value, loc, attw, out);
+      return msda::fwd_d32<TV>(s, pb, value, loc, attw, out);
     }
   }
   return msda::fwd_generic<TV, TA>(s, pb, value, loc, attw, out);
@@ -165,8 +164,8 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
     if constexpr (sizeof(TA) == 4) {
       static const bool no_pdl = getenv("MSDA_B200_NO_PDL") && atoi(getenv("MSDA_B200_NO_PDL")) != 0;
       // ... and the window kernel of encoder-sized problems, whose whole front end precedes its first reduction
-      const bool split = msda::use_split(pb);
-      const bool window = !split && !(pb.flags & (MSDA_FLAG_NO_WINDOW | MSDA_FLAG_BWD_HALVES | MSDA_FLAG_BWD_WS));
+      const int fam = msda::kernel_family(pb);
+      const bool split = fam == MSDA_KERNEL_SPLIT, window = fam == MSDA_KERNEL_WINDOW;
       pdl = !no_pdl && num_query > 0 && !det && !(pb.flags & MSDA_FLAG_FORCE_GENERIC) &&
             fast_shape(sizeof(TV), channels, num_levels, num_point) && fits_int32(pb.d) && (split || window) &&
             aligned(value, 16) && aligned(gv, 16) && aligned(loc, 16) && aligned(attw, 16) && aligned(grad_out, 16) &&
@@ -187,24 +186,18 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
                       aligned(value, 16) && aligned(gv, 16) && aligned(loc, 16) && aligned(attw, 16) &&
                       aligned(grad_out, 16) && aligned(gl, 16) && aligned(ga, 16);  // 16-byte vector loads / stores / reductions
     if (fast && no_gv) return msda::bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
-    // deterministic, large problem: the window kernel with canonical in-block order and fixed-point accumulation
-    if (fast && det && !msda::use_split(pb) && !(pb.flags & MSDA_FLAG_NO_WINDOW))
+    // deterministic, window-sized problem: the window kernel with canonical in-block order and fixed-point accumulation
+    const int fam = msda::kernel_family(pb);
+    if (fast && det && fam == MSDA_KERNEL_WINDOW)
       return msda::bwd_d32_win_det<TV>(s, pb, grad_out, value, loc, attw, gv, gl, ga, opts ? opts->workspace : nullptr,
                                        opts ? opts->workspace_bytes : 0);
     if (fast) {
-      // large problems: the fused window kernel (0.414 ms per bs=2 encoder layer).  MSDA_FLAG_BWD_HALVES runs
-      // the two halves of the backward as two kernels instead — gather + dot products for grad_sampling_loc /
-      // grad_attn_weight (0.200 ms), cell-sorted accumulation for grad_value (msda_d32_gv.cuh, 0.21 ms): no
-      // faster back to back (0.423 ms), kept because each half is useful alone (MSDA_FLAG_NO_GRAD_VALUE).
-      const bool large = !det && !msda::use_split(pb) && !(pb.flags & MSDA_FLAG_NO_WINDOW);
-      if (large && (pb.flags & MSDA_FLAG_BWD_HALVES)) {
-        rc = msda::bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
-        return rc != MSDA_OK ? rc : msda::gradvalue_d32<TV>(s, pb, grad_out, loc, attw, gv);
-      }
-      const bool window = large;
-      rc = window ? msda::bwd_d32_win<TV>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
-           : det  ? msda::bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
-                  : msda::bwd_d32<TV, true>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
+      // encoder-sized problems with a patch order: the shared-memory window kernel; otherwise the L1-gather kernels
+      // (split: warp per (query, head); tiled: lane group per (query, head)), which in deterministic mode leave
+      // grad_value to the sort-by-corner pass below
+      rc = (fam == MSDA_KERNEL_WINDOW && !det) ? msda::bwd_d32_win<TV>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
+           : det                                ? msda::bwd_d32<TV, false>(s, pb, grad_out, value, loc, attw, gv, gl, ga)
+                                                : msda::bwd_d32<TV, true>(s, pb, grad_out, value, loc, attw, gv, gl, ga);
       if (rc != MSDA_OK || !det) return rc;
     }
     if (det) {
@@ -220,10 +213,9 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
 
 // ---- fused prologue: large D=32 problems only, default kernels only ----------------------
 bool fused_supported(const Problem& pb, int dtype_bytes) {
-  const uint32_t bad = MSDA_FLAG_DETERMINISTIC | MSDA_FLAG_FORCE_GENERIC | MSDA_FLAG_NO_WINDOW | MSDA_FLAG_WINDOW_FWD |
-                       MSDA_FLAG_LDG256 | MSDA_FLAG_BWD_HALVES | MSDA_FLAG_BWD_WS | MSDA_FLAG_NO_GRAD_VALUE;
+  const uint32_t bad = MSDA_FLAG_DETERMINISTIC | MSDA_FLAG_FORCE_GENERIC | MSDA_FLAG_NO_GRAD_VALUE;
   return !(pb.flags & bad) && fast_shape(dtype_bytes, pb.d.channels, pb.d.num_levels, pb.d.num_point) &&
-         fits_int32(pb.d) && !msda::use_split(pb) && pb.d.batch > 0 && pb.d.num_query > 0;
+         fits_int32(pb.d) && msda::kernel_family(pb) == MSDA_KERNEL_WINDOW && pb.d.batch > 0 && pb.d.num_query > 0;
 }
 
 template <typename TV>

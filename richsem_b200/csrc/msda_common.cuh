@@ -147,22 +147,11 @@ __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
 __device__ __forceinline__ void st_stream_f2(float* p, float2 v) {
   asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
-// 32-byte (256-bit) global accesses, new with sm_100: one LDG.E.256 moves a quarter of a 128-byte fp32
-// row per lane, so a warp instruction covers 8 rows (p must be 32-byte aligned).
-__device__ __forceinline__ void ldg256_nc(const float* p, float2 (&v)[4]) {
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x),
-                 "=f"(v[3].y)
-               : "l"(p));
-}
-__device__ __forceinline__ void st_stream_256(float* p, const float2 (&v)[4]) {
-  asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0].x), "f"(v[0].y), "f"(v[1].x),
-               "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y)
-               : "memory");
-}
-// 16-byte fp32 vector reduction: one REDG.E.ADD.F32x4 per lane (sm_90+).
+// 16-byte fp32 vector reduction: one REDG.E.ADD.F32x4 per lane (sm_90+).  No "memory" clobber: the kernels never
+// read grad_value, and with the clobber the compiler could not hoist the next corner's row load above the
+// previous corner's reduction (a chain of dependent L2 round trips, profiles/r2_bwd_window_phase_budget.md).
+// volatile keeps the reductions in program order relative to griddepcontrol.wait.
 __device__ __forceinline__ void red_add_f4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 

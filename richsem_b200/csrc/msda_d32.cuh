@@ -307,108 +307,6 @@ msda_fwd_d32_kernel(const VT* __restrict__ value, const float* __restrict__ loc,
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// forward, fp32 value, 256-bit gathers: 4 lanes x 8 channels per (query, head), so a warp serves 8
-// pairs and every gather instruction (LDG.E.256) covers 8 rows; the blends are packed FFMA2.
-// Against the 8-lane kernel above this halves the non-FMA instructions per sample (address
-// arithmetic, predicates, record reads) and the FMA instructions.  An L1-resident row gather sustains
-// 1.2 cycles per row with LDG.128 and 1.08 with LDG.256 (scratch/gather256.cu), but at the headline shape
-// this kernel is no faster than the 8-lane one (0.147 vs 0.142 ms): the forward is co-limited by the L1
-// data path and instruction issue, so it is opt-in (MSDA_FLAG_LDG256).
-// Requires a 32-byte aligned value / out.
-// ------------------------------------------------------------------------------------------
-template <int LP>
-struct D32x8Cfg {
-  static constexpr int G = 4, C = 8, GPW = 8;
-  static constexpr int QPP = kWarps * GPW;
-  static constexpr int PASSES = kTileQ / QPP;
-  static constexpr int REC_STRIDE = LP + 1;
-  static constexpr int SMEM_BYTES = kWarps * GPW * REC_STRIDE * 16;
-  static_assert(kTileQ % QPP == 0, "tile must be a whole number of passes");
-};
-
-template <int kL, int kP, int kM>
-__global__ void __launch_bounds__(kThreads)
-msda_fwd_d32_f32x8_kernel(const float* __restrict__ value, const float* __restrict__ loc,
-                          const float* __restrict__ attw, float* __restrict__ out,
-                          const int* __restrict__ order, const int order_len,
-                          const __grid_constant__ MsdaLevels lv, const int S, const int M_rt, const int Lq) {
-  constexpr int LP = kL * kP;
-  using Cfg = D32x8Cfg<LP>;
-  constexpr int G = Cfg::G, C = Cfg::C;
-  extern __shared__ float4 smem[];
-  const int M = kM ? kM : M_rt;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane / G, j = lane % G;
-  const int m = blockIdx.x % M;
-  const int tile = blockIdx.x / M;
-  const int b = blockIdx.y;
-  const int M32 = M * 32;
-
-  float4* rec = smem + (warp * Cfg::GPW + g) * Cfg::REC_STRIDE;
-  const float* value_b = value + (size_t)b * S * M32 + j * C;
-
-#pragma unroll 1
-  for (int pass = 0; pass < Cfg::PASSES; ++pass) {
-    const int slot = tile * kTileQ + pass * Cfg::QPP + warp * Cfg::GPW + g;
-    int q = -1;
-    if (slot < order_len) q = order ? order[slot] : slot;
-    const bool active = q >= 0;
-    const size_t qm = ((size_t)b * Lq + (active ? q : 0)) * M + m;
-
-    if (active) d32_decode_points<G, kL, kP>(loc, attw, qm, j, m, M, lv, rec);
-    __syncwarp();
-
-    if (active) {
-      float2 acc[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int p = 0; p < LP; ++p) {
-        const int l = p / kP;
-        const float4 r = rec[p];
-        const int bm = __float_as_int(r.x);
-        const float lh = r.y, lw = r.z, a = r.w;
-        const float a_hh = a * (1.f - lh), a_lh = a * lh, hw = 1.f - lw;
-        const float* p0 = value_b + (ptrdiff_t)(bm & ~31);
-        const float* p2 = p0 + (ptrdiff_t)(lv.W[l] * M32);
-        float2 v[4];
-        if (bm & 1) {
-          ldg256_nc(p0, v);
-          const float w = a_hh * hw;
-          const float2 w2 = make_float2(w, w);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[c] = ffma2(w2, v[c], acc[c]);
-        }
-        if (bm & 2) {
-          ldg256_nc(p0 + M32, v);
-          const float w = a_hh * lw;
-          const float2 w2 = make_float2(w, w);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[c] = ffma2(w2, v[c], acc[c]);
-        }
-        if (bm & 4) {
-          ldg256_nc(p2, v);
-          const float w = a_lh * hw;
-          const float2 w2 = make_float2(w, w);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[c] = ffma2(w2, v[c], acc[c]);
-        }
-        if (bm & 8) {
-          ldg256_nc(p2 + M32, v);
-          const float w = a_lh * lw;
-          const float2 w2 = make_float2(w, w);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[c] = ffma2(w2, v[c], acc[c]);
-        }
-      }
-      st_stream_256(out + qm * 32 + j * C, acc);
-    }
-    __syncwarp();
-  }
-}
-
 // Reduce-scatter of v[0..G) over the G lanes of a group: returns, in lane j, the sum over the
 // group's lanes of v[j].  G-1 shuffles instead of the G*log2(G) of G separate butterflies.
 template <int G>

@@ -24,23 +24,29 @@ struct Problem {
   const int32_t* order;
   int order_len;
   uint32_t flags;
+  int kernel_hint;  // MSDA_KERNEL_*
   MsdaFused fz;  // ref_dim 0: the reference op; 2 | 4: fused prologue (loc / attw are the raw Linear outputs)
   // the library's own zero-fill kernel of grad_value is the launch right before the backward kernel on this stream: the
   // backward may start early (programmatic dependent launch) and waits (griddepcontrol.wait) before its first reduction
   bool pdl_after_fill;
 };
 
-// Few (query, head) pairs (decoder cross-attention): one warp per pair instead of one lane group.
-inline bool use_split(const Problem& pb) {
-  return !(pb.flags & MSDA_FLAG_NO_SPLIT) &&
-         (long long)pb.d.batch * pb.d.num_query * pb.d.num_heads <= 65536 && pb.d.num_levels >= 2 &&
-         pb.d.num_levels <= 6;
+// Kernel family of a head_dim-32 problem (MSDA_KERNEL_*).  Few (query, head) pairs (decoder cross-attention): one
+// warp per pair (split).  Large problems: the backward's shared-memory window kernel needs spatially coherent
+// tiles of 64 queries, i.e. the host's patch order (encoder self-attention); without an order the samples of a
+// tile scatter over the whole map and the tiled L1-gather kernel is the better fit.
+inline int kernel_family(const Problem& pb) {
+  if (pb.kernel_hint == MSDA_KERNEL_SPLIT) return MSDA_KERNEL_SPLIT;
+  if (pb.kernel_hint == MSDA_KERNEL_TILED || pb.kernel_hint == MSDA_KERNEL_WINDOW) return pb.kernel_hint;
+  if ((long long)pb.d.batch * pb.d.num_query * pb.d.num_heads <= 65536) return MSDA_KERNEL_SPLIT;
+  return pb.order ? MSDA_KERNEL_WINDOW : MSDA_KERNEL_TILED;
 }
+inline bool use_split(const Problem& pb) { return kernel_family(pb) == MSDA_KERNEL_SPLIT; }
 
 // Zero-fill of grad_value as a kernel (16-byte stores) that lets the next kernel on the stream launch early.
 int zero_fill_pdl(cudaStream_t s, float* p, size_t bytes);
 
-// ---- head_dim 32, 4 points, 1..6 levels; VT = float | __nv_bfloat16 (explicitly instantiated) ----
+// ---- head_dim 32, 4 points, 3..5 levels; VT = float | __nv_bfloat16 (explicitly instantiated) ----
 // msda_launch_d32.cu: L1-gather kernels (tiled for large problems, split for small ones).
 template <typename VT>
 int fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const float* loc, const float* attw, VT* out);
@@ -48,8 +54,6 @@ template <typename VT, bool kScatter>
 int bwd_d32(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
             const float* attw, float* gv, float* gl, float* ga);
 // msda_launch_win.cu: shared-memory window kernels (large problems).
-template <typename VT>
-int fwd_d32_win(cudaStream_t s, const Problem& pb, const VT* value, const float* loc, const float* attw, VT* out);
 template <typename VT>
 int bwd_d32_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
                 const float* attw, float* gv, float* gl, float* ga);
@@ -59,10 +63,6 @@ int bwd_d32_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* value
 template <typename VT>
 int bwd_d32_win_det(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, const float* loc,
                     const float* attw, float* gv, float* gl, float* ga, void* workspace, size_t workspace_bytes);
-// grad_value alone, by cell-sorted accumulation (msda_d32_gv.cuh); pairs with bwd_d32<VT, false>.
-template <typename VT>
-int gradvalue_d32(cudaStream_t s, const Problem& pb, const VT* go, const float* loc, const float* attw, float* gv);
-
 // ---- msda_launch_other.cu: any-shape kernels, deterministic grad_value, index probe ----
 template <typename TV, typename TA>
 int fwd_generic(cudaStream_t s, const Problem& pb, const TV* value, const TA* loc, const TA* attw, TV* out);

@@ -18,17 +18,6 @@ int launch_fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const flo
       pb.d.num_query, pb.fz);
   return after_launch("msda_fwd_d32_kernel");
 }
-template <int kL, int kM>
-int launch_fwd_d32_x8(cudaStream_t s, const Problem& pb, const float* value, const float* loc,
-                      const float* attw, float* out) {
-  using Cfg = msda::D32x8Cfg<kL * 4>;
-  const int tiles = (pb.order_len + msda::kTileQ - 1) / msda::kTileQ;
-  dim3 grid(tiles * pb.d.num_heads, pb.d.batch);
-  msda::msda_fwd_d32_f32x8_kernel<kL, 4, kM><<<grid, msda::kThreads, Cfg::SMEM_BYTES, s>>>(
-      value, loc, attw, out, pb.order, pb.order_len, pb.lv, pb.d.spatial_size, pb.d.num_heads,
-      pb.d.num_query);
-  return after_launch("msda_fwd_d32_f32x8_kernel");
-}
 template <typename VT, int kL, int kM, bool kScatter>
 int launch_bwd_d32(cudaStream_t s, const Problem& pb, const VT* grad_out, const VT* value,
                    const float* loc, const float* attw, float* gv, float* gl, float* ga) {
@@ -81,12 +70,9 @@ int launch_bwd_split(cudaStream_t s, const Problem& pb, const VT* grad_out, cons
 
 #define MSDA_SWITCH_L(L_, CALL)                                                              \
   switch (L_) {                                                                              \
-    case 1: return CALL(1);                                                                  \
-    case 2: return CALL(2);                                                                  \
     case 3: return CALL(3);                                                                  \
     case 4: return CALL(4);                                                                  \
     case 5: return CALL(5);                                                                  \
-    case 6: return CALL(6);                                                                  \
     default: return fail(MSDA_ERR_UNSUPPORTED, "no tuned kernel for num_levels=%d", L_);      \
   }
 
@@ -101,20 +87,8 @@ int fwd_d32(cudaStream_t s, const Problem& pb, const VT* value, const float* loc
     MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL
   }
-  // fp32 value, 32-byte aligned: 256-bit gathers, 4 lanes per (query, head).  Opt-in: half the instructions
-  // of the 128-bit kernel but no faster on B200 (0.147 ms against 0.142 ms per bs=2 encoder layer) — the
-  // forward waits on L1 misses, not on instruction issue.
-  if constexpr (sizeof(VT) == 4) {
-    if ((pb.flags & MSDA_FLAG_LDG256) && ((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(out)) & 31) == 0) {
-      if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_fwd_d32_x8<4, 8>(s, pb, value, loc, attw, out);
-#define CALL(L) launch_fwd_d32_x8<L, 0>(s, pb, value, loc, attw, out)
-      MSDA_SWITCH_L(pb.d.num_levels, CALL)
-#undef CALL
-    }
-  }
-  // the DINO / RichSem configuration (8 heads, 4 or 5 levels) gets the head count baked in
+  // the DINO / RichSem configuration (8 heads, 4 levels) gets the head count baked in
   if (pb.d.num_heads == 8 && pb.d.num_levels == 4) return launch_fwd_d32<VT, 4, 8>(s, pb, value, loc, attw, out);
-  if (pb.d.num_heads == 8 && pb.d.num_levels == 5) return launch_fwd_d32<VT, 5, 8>(s, pb, value, loc, attw, out);
 #define CALL(L) launch_fwd_d32<VT, L, 0>(s, pb, value, loc, attw, out)
   MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL
@@ -131,8 +105,6 @@ int bwd_d32(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, co
   }
   if (pb.d.num_heads == 8 && pb.d.num_levels == 4)
     return launch_bwd_d32<VT, 4, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
-  if (pb.d.num_heads == 8 && pb.d.num_levels == 5)
-    return launch_bwd_d32<VT, 5, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
 #define CALL(L) launch_bwd_d32<VT, L, 0, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
   MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL

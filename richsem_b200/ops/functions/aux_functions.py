@@ -38,7 +38,7 @@ def _shapes_host(spatial_shapes):
     if not isinstance(spatial_shapes, torch.Tensor):
         flat = [int(x) for hw in spatial_shapes for x in hw]
         return (ctypes.c_int64 * len(flat))(*flat)
-    key = (id(spatial_shapes), spatial_shapes._version)
+    key = (id(spatial_shapes), -1 if spatial_shapes.is_inference() else spatial_shapes._version)
     hit = _shapes_cache.get(key)
     if hit is not None and hit[1]() is spatial_shapes:
         return hit[0]

@@ -9,9 +9,9 @@ for kind, lq in (("E", None), ("U", 300), ("Dn", 200)):
         if kind == "U":
             i["loc"] = (i["loc"] * 1.5 - 0.25).contiguous()
         a = (i["value"], i["shapes"], i["starts"], i["loc"], i["attw"])
-        for fl in (0, _capi.FLAG_NO_SPLIT, _capi.FLAG_NO_SPLIT | _capi.FLAG_WINDOW_FWD, _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW,
-                   _capi.FLAG_NO_SPLIT | _capi.FLAG_LDG256 | _capi.FLAG_NO_WINDOW, _capi.FLAG_AGGREGATE | _capi.FLAG_NO_SPLIT):
-            o = ext.ms_deform_attn_forward(*a, 64, _flags=fl)
-            g = ext.ms_deform_attn_backward(*a, i["grad_out"], 64, _flags=fl)
+        for kern in (_capi.KERNEL_AUTO, _capi.KERNEL_SPLIT, _capi.KERNEL_TILED, _capi.KERNEL_WINDOW):
+            for fl in (0, _capi.FLAG_DETERMINISTIC):
+                o = ext.ms_deform_attn_forward(*a, 64, _kernel=kern)
+                g = ext.ms_deform_attn_backward(*a, i["grad_out"], 64, _flags=fl, _kernel=kern)
 torch.cuda.synchronize()
 print("ok")

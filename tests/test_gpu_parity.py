@@ -39,8 +39,16 @@ def test_extension_is_loaded_from_the_tree():
     assert _capi.launch_count() == before + 1
 
 
+def _path(path):
+    """Keyword arguments that put a (small) test problem through one kernel family (msda_opts.kernel_hint)."""
+    from richsem_b200 import _capi
+
+    return {"auto": {}, "split": {"_kernel": _capi.KERNEL_SPLIT}, "window": {"_kernel": _capi.KERNEL_WINDOW},
+            "tiled": {"_kernel": _capi.KERNEL_TILED}, "generic": {"_flags": _capi.FLAG_FORCE_GENERIC}}[path]
+
+
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-@pytest.mark.parametrize("path", ["auto", "halves", "window", "ws", "tiled", "tiled256", "generic"])
+@pytest.mark.parametrize("path", ["auto", "window", "tiled", "generic"])
 def test_golden_forward_backward(case, path):
     """auto = what the library picks (warp-per-query "split" kernels at these sizes for D=32);
     window = the shared-memory window kernels used for large problems; tiled = their L1-gather
@@ -50,14 +58,8 @@ def test_golden_forward_backward(case, path):
     g = load_golden(case)
     f64 = g["value"].dtype == torch.float64
     v, shp, st, loc, w, go = _to_dev(g)
-    flags = {"auto": 0, "halves": _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_HALVES,
-             "window": _capi.FLAG_NO_SPLIT | _capi.FLAG_WINDOW_FWD,
-             "ws": _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_WS,
-             "tiled": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW,
-             "tiled256": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW | _capi.FLAG_LDG256,
-             "generic": _capi.FLAG_FORCE_GENERIC}[path]
-    out = _ext().ms_deform_attn_forward(v, shp, st, loc, w, 64, _flags=flags)
-    gv, gl, ga = _ext().ms_deform_attn_backward(v, shp, st, loc, w, go, 64, _flags=flags)
+    out = _ext().ms_deform_attn_forward(v, shp, st, loc, w, 64, **_path(path))
+    gv, gl, ga = _ext().ms_deform_attn_backward(v, shp, st, loc, w, go, 64, **_path(path))
     ft, bt = (1e-12, 1e-11) if f64 else (FWD_TOL, BWD_TOL)
     assert rel_err(out.cpu(), g["out"]) < ft
     assert rel_err(gv.cpu(), g["grad_value"]) < bt
@@ -138,24 +140,22 @@ def test_gradcheck_like_reference(channels):
     assert gradcheck(MSDeformAttnFunction.apply, (value, shapes, starts, loc, w, 2))
 
 
-@pytest.mark.parametrize("kind,n,lq,bflags", [("E", 1, None, 0), ("E", 2, None, "ws"), ("E", 1, None, "halves"), ("E", 1, None, "tiled"),
-                                              ("U", 2, 3000, "ws"),
-                                              ("U", 2, 3000, 0), ("U", 2, 3000, "halves"), ("U", 2, 3000, "window"),
-                                              ("Dn", 2, 1100, 0), ("Dn", 2, 1100, "window")])
+@pytest.mark.parametrize("kind,n,lq,bflags", [("E", 1, None, "auto"), ("E", 2, None, "auto"), ("E", 1, None, "tiled"),
+                                              ("U", 2, 3000, "auto"), ("U", 2, 3000, "tiled"), ("U", 2, 3000, "window"),
+                                              ("U", 2, 9000, "auto"),
+                                              ("Dn", 2, 1100, "auto"), ("Dn", 2, 1100, "window")])
 def test_dino_shape_against_c_oracle(kind, n, lq, bflags, c_oracle):
     """Full DINO 4-scale R50 800x1333 pyramid (S=22223, M=8, D=32, L=4, P=4) against the C oracle.
-    Large problems ("E"; "U" with 3000 queries: no locality, most levels fall back to direct reductions)
-    take the fused window backward by default; "halves" = gather kernel + cell-sorted grad_value kernel,
-    "tiled" = per-corner reductions, "window" = the fused window kernel forced on small / non-local inputs."""
+    Encoder self-attention ("E", patch order) takes the window backward; "U" with 3000 queries takes the split
+    kernels, with 9000 the tiled ones (large, no query order); "tiled" = per-corner reductions forced,
+    "window" = the window kernel forced on small / non-local inputs (most levels fall back to its direct pass)."""
     from richsem_b200 import _capi, synthetic as syn
 
-    bflags = {0: 0, "window": _capi.FLAG_NO_SPLIT, "ws": _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_WS, "halves": _capi.FLAG_BWD_HALVES | _capi.FLAG_NO_SPLIT,
-              "tiled": _capi.FLAG_NO_WINDOW}[bflags]
     shapes = syn.level_shapes(800, 1333)
     i = syn.make_inputs(kind, n, shapes, "cuda:0", seed=21, lq=lq)
     out = _ext().ms_deform_attn_forward(i["value"], i["shapes"], i["starts"], i["loc"], i["attw"], 64)
     gv, gl, ga = _ext().ms_deform_attn_backward(i["value"], i["shapes"], i["starts"], i["loc"], i["attw"],
-                                                i["grad_out"], 64, _flags=bflags)
+                                                i["grad_out"], 64, **_path(bflags))
     v, loc, w, go = (i[k].cpu() for k in ("value", "loc", "attw", "grad_out"))
     want = c_oracle.forward(v, shapes, loc, w)
     assert rel_err(out.cpu(), want) < FWD_TOL
@@ -177,12 +177,12 @@ def test_query_order_does_not_change_results(monkeypatch):
     from richsem_b200 import _capi
 
     args = (i["value"], i["shapes"], i["starts"], i["loc"], i["attw"])
-    nosplit = _capi.FLAG_NO_SPLIT
-    a = _ext().ms_deform_attn_forward(*args, 64, _flags=nosplit)
-    ga = _ext().ms_deform_attn_backward(*args, i["grad_out"], 64, _flags=nosplit)
+    win = {"_kernel": _capi.KERNEL_WINDOW}
+    a = _ext().ms_deform_attn_forward(*args, 64, **win)
+    ga = _ext().ms_deform_attn_backward(*args, i["grad_out"], 64, **win)
     monkeypatch.setenv("MSDA_B200_QUERY_ORDER", "natural")
-    b = _ext().ms_deform_attn_forward(*args, 64, _flags=nosplit)
-    gb = _ext().ms_deform_attn_backward(*args, i["grad_out"], 64, _flags=nosplit)
+    b = _ext().ms_deform_attn_forward(*args, 64, **win)
+    gb = _ext().ms_deform_attn_backward(*args, i["grad_out"], 64, **win)
     assert torch.equal(a, b)                       # forward: each (q, m) is summed in the same order
     # the order decides which levels a block serves from its shared-memory window, and the windowed
     # and direct backward paths reduce over lanes in different orders
@@ -225,7 +225,10 @@ def test_deterministic_window_backward_large_problem(kind, dtype, c_oracle):
     if kind == "U":
         i["loc"] = (i["loc"] * 1.3 - 0.15).contiguous()
     args = (i["value"], i["shapes"], i["starts"], i["loc"], i["attw"], i["grad_out"], 64)
-    b = _ext().ms_deform_attn_backward
+    # "U" has no query order (Lq != S): the window kernel is forced, so that its direct pass is covered too
+    kw = {} if kind == "E" else {"_kernel": _capi.KERNEL_WINDOW}
+    b0 = _ext().ms_deform_attn_backward
+    b = lambda *a, **k: b0(*a, **k, **kw)
     d1 = b(*args, _flags=_capi.FLAG_DETERMINISTIC)
     d2 = b(*args, _flags=_capi.FLAG_DETERMINISTIC)
     at = b(*args)
@@ -281,28 +284,23 @@ def test_window_backward_matches_tiled_backward_bf16_and_five_levels():
                           ([(33, 47), (17, 24), (9, 12), (5, 6), (3, 3)], torch.float32)):
         i = syn.make_inputs("E", 2, shapes, "cuda:0", seed=4, dtype=dtype)
         args = (i["value"], i["shapes"], i["starts"], i["loc"], i["attw"], i["grad_out"], 64)
-        y = b(*args, _flags=_capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW)
-        for fl in (_capi.FLAG_NO_SPLIT, _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_HALVES, _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_WS):
-            x = b(*args, _flags=fl)
-            assert rel_err(x[0], y[0]) < 1e-5
-            assert rel_err(x[1], y[1]) < 1e-5 and rel_err(x[2], y[2]) < 1e-5
+        y = b(*args, _kernel=_capi.KERNEL_TILED)
+        x = b(*args, _kernel=_capi.KERNEL_WINDOW)
+        assert rel_err(x[0], y[0]) < 1e-5
+        assert rel_err(x[1], y[1]) < 1e-5 and rel_err(x[2], y[2]) < 1e-5
 
 
-@pytest.mark.parametrize("path", ["auto", "halves", "window", "tiled", "generic"])
+@pytest.mark.parametrize("path", ["auto", "window", "tiled", "generic"])
 def test_bf16_value_variant(c_oracle, path):
     from richsem_b200 import _capi, synthetic as syn
 
-    flags = {"auto": 0, "halves": _capi.FLAG_NO_SPLIT | _capi.FLAG_BWD_HALVES,
-             "window": _capi.FLAG_NO_SPLIT | _capi.FLAG_WINDOW_FWD,
-             "tiled": _capi.FLAG_NO_SPLIT | _capi.FLAG_NO_WINDOW,
-             "generic": _capi.FLAG_FORCE_GENERIC}[path]
     shapes = syn.level_shapes(800, 1333)
     i = syn.make_inputs("Dn", 2, shapes, "cuda:0", seed=31, lq=1100)
     vb, gob = i["value"].bfloat16(), i["grad_out"].bfloat16()
-    out = _ext().ms_deform_attn_forward(vb, i["shapes"], i["starts"], i["loc"], i["attw"], 64, _flags=flags)
+    out = _ext().ms_deform_attn_forward(vb, i["shapes"], i["starts"], i["loc"], i["attw"], 64, **_path(path))
     assert out.dtype == torch.bfloat16
     gv, gl, ga = _ext().ms_deform_attn_backward(vb, i["shapes"], i["starts"], i["loc"], i["attw"], gob, 64,
-                                                _flags=flags)
+                                                **_path(path))
     assert gv.dtype == torch.float32 and gl.dtype == torch.float32 and ga.dtype == torch.float32
     # oracle in fp32 on the UNROUNDED inputs: the 1e-2 budget covers bf16 storage of value/out/grad_out
     v, loc, w, go = (i[k].cpu() for k in ("value", "loc", "attw", "grad_out"))
