@@ -3,13 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
-Workloads (all M=8, D=32, L=4, P=4, synthetic tensors, DINO 4-scale R50 800x1333 pyramid):
+Workloads (all M=8, D=32, L=4, P=4, synthetic tensors, DINO 4-scale R50 pyramid):
   encoder6   (default; BASELINE configs[1]) six deformable-encoder layers' MSDeformAttn, bs=2 per GPU,
              Lq=S=22,223, fp32, encoder-realistic locations "E"; one step = 6 forwards then 6 backwards
              on six distinct input sets (960 MB > L2, so no layer finds its inputs cached).
   decoder6   (configs[2]) six decoder cross-attention layers, bs=2, Lq=1100, bf16 value, locations "Dn".
   encoder1_hr1333 / encoder1_hr2000   (configs[4]) one encoder layer at 1333x1333 / 1600x2000.
-Add --deterministic for the sort-by-corner grad_value mode.
+  encoder_layer_ddp   (configs[3]) the whole encoder-layer train step under DDP.
+Add --deterministic for the bitwise-reproducible grad_value mode, --graph to replay the step from a CUDA graph.
+
+The DEFAULT invocation (no --workload) times encoder6 for the headline line and then appends, in the same JSON
+line, "workloads": every other BASELINE config (decoder6 eager and graph-replayed, the two high-resolution
+shapes, atomic and deterministic, and the DDP encoder-layer step — on every N, 1 included), each with its own
+value / ms_per_step / roofline / clocks, and "legacy_cuda": the reference's own CUDA kernels (recompiled for
+sm_100a, oracle/_ref) timed on the same B200 and the same inputs — a comparator leg outside the product's timed
+region.  --no-extra skips both.
 
 One process per GPU (torchrun for N>1); the op never communicates (images are independent), so ranks
 only meet at the barriers around the timed region; value = queries processed by all ranks / max-over-ranks
@@ -17,12 +25,15 @@ device time.  Prints ONE JSON line on rank 0.
 
 --impl reference times the reference's CPU path for this op — ms_deform_attn_core_pytorch (grid_sample)
 forward + autograd backward, restated in oracle/msda_oracle.py because /root/reference does not travel to
-the GPU box — on the host cores, rank 0 only.
+the GPU box — on the host cores, rank 0 only.  It never imports the richsem_b200 package (whose import loads
+the CUDA library): the synthetic-input module is loaded by file path.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -30,6 +41,7 @@ import sys
 import threading
 import time
 from pathlib import Path
+from types import SimpleNamespace
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
@@ -52,6 +64,14 @@ WORKLOADS = {
     # captured in one CUDA graph; --eager replays it launch by launch instead
     "encoder_stack6": ((800, 1333), 6, 2, "stack", None, "f32"),
 }
+# what the default invocation appends to the headline line: key -> (workload, options)
+EXTRA = [
+    ("decoder6", "decoder6", {}),
+    ("decoder6_graph", "decoder6", {"graph": True}),
+    ("encoder1_hr1333", "encoder1_hr1333", {}),
+    ("encoder1_hr2000", "encoder1_hr2000", {}),
+    ("encoder1_hr2000_deterministic", "encoder1_hr2000", {"deterministic": True}),
+]
 
 
 def parse_args():
@@ -63,7 +83,8 @@ def parse_args():
     ap.add_argument("--workload", default="encoder6", choices=sorted(WORKLOADS))
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--lib-flags", type=lambda x: int(x, 0), default=0,
-                    help="extra MSDA_FLAG_* bits for forward and backward (kernel-selection experiments)")
+                    help="extra MSDA_FLAG_* bits for forward and backward (experiments)")
+    ap.add_argument("--kernel", type=int, default=0, help="msda_opts.kernel_hint (MSDA_KERNEL_*; experiments)")
     ap.add_argument("--graph", action="store_true", help="op workloads: capture one step (all forwards + backwards) in a "
                     "CUDA graph and replay it; matters for decoder-sized calls, whose kernels (14-36 us) are shorter "
                     "than the Python launch path.  Per-launch times are then not available: the roofline is the step's")
@@ -75,7 +96,7 @@ def parse_args():
     ap.add_argument("--padding", action="store_true", help="encoder_stack6: image 1 of each pair is padded (mask path)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the additional workloads / comparator legs of the default line")
+    ap.add_argument("--no-extra", action="store_true", help="skip the additional workloads / comparator leg of the default line")
     ap.add_argument("--e2e-steps", type=int, default=12)
     return ap.parse_args()
 
@@ -90,6 +111,31 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_synthetic():
+    """richsem_b200/synthetic.py loaded by PATH: importing the package would dlopen libmsda_b200.so, which the CPU
+    reference arm must not do (the module itself needs torch only)."""
+    spec = importlib.util.spec_from_file_location("_msda_synthetic", ROOT / "richsem_b200" / "synthetic.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def workload_config(name, syn):
+    """The workload-defining part of `config`, identical in both arms (product and --impl reference)."""
+    hw, layers, bs, kind, lq, vdt = WORKLOADS[name]
+    shapes = syn.level_shapes(*hw)
+    S = sum(h * w for h, w in shapes)
+    return {"workload": name, "image": f"{hw[0]}x{hw[1]}", "levels": [list(s) for s in shapes], "S": S,
+            "Lq": S if lq is None else lq, "batch_per_gpu": bs, "layers_per_step": layers, "heads": 8, "head_dim": 32,
+            "points": 4, "locations": {"layer": "E", "stack": "E"}.get(kind, kind), "value_dtype": vdt,
+            "queries_per_step_per_gpu": layers * bs * (S if lq is None else lq),
+            "unit_of_value": "queries/s = queries processed / time; a product step processes queries_per_step_per_gpu "
+                             "queries per GPU, a step of the CPU reference arm a bounded sample of them (one layer of "
+                             "one image) — the per-query rate is what both arms report",
+            "l2_policy": f"{layers} distinct input set(s) per step, visited round-robin; a step's inputs and outputs "
+                         "exceed the 126 MB L2, so no layer finds its operands cached; no explicit flush"}
+
+
 # --------------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi in the background during the timed region)
 # --------------------------------------------------------------------------------------------
@@ -97,26 +143,35 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, interval_ms=50):
+        self.index, self.proc, self.lines, self.interval = index, None, [], interval_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", str(self.interval)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=2.0):
+        """Blocks until nvidia-smi has delivered its first sample, so that a short timed region is not over before
+        the sampler runs."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, since=None):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.06)  # let a sample taken at the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -124,7 +179,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if since is not None and ts < since:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -142,29 +199,32 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's CPU path (grid_sample), bounded sample
 # --------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, hw=(800, 1333)):
-    """One step = one encoder layer, bs=1, fp32, fwd + autograd bwd (BASELINE configs[0]) on all host cores."""
+def cpu_reference_run(steps, warmup, hw=(800, 1333), n_sets=1):
+    """One step = one encoder layer of ONE image (bs=1), fp32, fwd + autograd bwd of the reference's CPU path
+    (BASELINE configs[0]) on all host cores; steps visit `n_sets` distinct input sets round-robin."""
     import torch
 
     from oracle.msda_oracle import core_pytorch_fwd_bwd
-    from richsem_b200 import synthetic as syn
 
+    syn = load_synthetic()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     shapes = syn.level_shapes(*hw)
-    i = syn.make_inputs("E", 1, shapes, "cpu", seed=1234)
+    sets = [syn.make_inputs("E", 1, shapes, "cpu", seed=1234 + k) for k in range(max(1, n_sets))]
     times = []
     for it in range(warmup + steps):
+        i = sets[it % len(sets)]
         t0 = time.perf_counter()
         core_pytorch_fwd_bwd(i["value"], shapes, i["loc"], i["attw"], i["grad_out"])
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     total = sum(times)
-    qps = steps * i["Lq"] / total
+    qps = steps * sets[0]["Lq"] / total
     return dict(value=qps, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample=f"{steps} x (one encoder layer, bs=1, Lq=S={i['Lq']}, fp32, fwd+autograd bwd of the "
-                       f"grid_sample formulation), {warmup} warm-up, {total:.1f} s timed",
+                sample=f"{steps} steps x (one encoder layer of one image: bs=1, Lq=S={sets[0]['Lq']}, fp32, fwd + autograd "
+                       f"bwd of the grid_sample formulation = ms_deform_attn_core_pytorch restated in oracle/, "
+                       f"bit-identical), {len(sets)} input set(s) round-robin, {warmup} warm-up, {total:.1f} s timed",
                 ms_per_step=1e3 * total / steps)
 
 
@@ -172,25 +232,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    syn = load_synthetic()
+    # the driver's K and W are honoured; a step is a bounded sample (one layer of one image, ~0.3 s on 16 cores), so
+    # that K = 20 ends within seconds; a very large K is capped to keep the run within minutes
+    steps, warmup = max(1, min(args.steps, 400)), max(0, min(args.warmup, 20))
     hw, layers, bs, kind, lq, vdt = WORKLOADS[args.workload]
     hw = hw if kind == "E" else (800, 1333)
-    r = cpu_reference_run(steps, warmup, hw)
-    from richsem_b200 import synthetic as syn
-
-    shapes = syn.level_shapes(*hw)
-    S = sum(h * w for h, w in shapes)
+    r = cpu_reference_run(steps, warmup, hw, n_sets=layers)
     line = {
         "metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "image": f"{hw[0]}x{hw[1]}", "levels": shapes, "S": S, "Lq": S,
-                   "batch_per_gpu": bs, "layers_per_step": layers, "heads": 8, "head_dim": 32, "points": 4,
-                   "locations": "E", "grad_value_mode": "autograd of grid_sample",
-                   "parallelism": "rank 0 only, all host cores",
-                   "sample": "each step = ONE encoder layer at bs=1 of this workload (a bounded sample: the CPU path "
-                             "needs ~0.3 s per layer-image), reference op = grid_sample formulation "
-                             "(ms_deform_attn_core_pytorch restated in oracle/, bit-identical)"},
+        "config": workload_config(args.workload, syn),
+        "arm": {"parallelism": "rank 0 only, all host cores", "grad_value_mode": "autograd of grid_sample",
+                "step": "a bounded sample of the workload's step: ONE encoder layer of ONE image per step (the CPU "
+                        "path needs ~0.3 s for it); value is the per-query rate, comparable across arms"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -222,6 +278,209 @@ def aggregate_qps(queries_per_rank_step, world, ms_per_step):
     return world * queries_per_rank_step / (ms_per_step * 1e-3)
 
 
+def sync_all(c):
+    if c.world > 1:
+        c.dist.barrier()
+    c.torch.cuda.synchronize()
+
+
+# --------------------------------------------------------------------------------------------
+# B200 arm: one op workload
+# --------------------------------------------------------------------------------------------
+def time_op_workload(c, name, steps, warmup, graph=False, deterministic=False, lib_flags=0, kernel=0, want_e2e=False,
+                     e2e_steps=12, min_seconds=0.0, keep_sets=None):
+    """Times `steps` steps of an op workload on every rank.  min_seconds > 0 (the additional workloads of the default
+    line): the step count is raised so that the timed region lasts at least that long — their steps are a few hundred
+    microseconds, and a region that short would be over before nvidia-smi delivers one clocks sample."""
+    torch, ext, _capi, syn = c.torch, c.ext, c._capi, c.syn
+    hw, layers, bs, kind, lq, vdt = WORKLOADS[name]
+    shapes = syn.level_shapes(*hw)
+    tdt = torch.bfloat16 if vdt == "bf16" else torch.float32
+    sets = [syn.make_inputs(kind, bs, shapes, c.dev, seed=rank_seed(1234, c.rank, i), lq=lq, dtype=tdt) for i in range(layers)]
+    S, Lq = sets[0]["S"], sets[0]["Lq"]
+    shp, st = sets[0]["shapes"], sets[0]["starts"]
+    queries_per_step = layers * bs * Lq
+    flags = (_capi.FLAG_DETERMINISTIC if deterministic else 0) | lib_flags
+    vb = 2 if vdt == "bf16" else 4
+    fwd_bytes, bwd_bytes = syn.algorithmic_bytes(bs, S, Lq, value_bytes=vb, out_bytes=vb)
+    in_bytes = sum(s[k].numel() * s[k].element_size() for s in sets for k in ("value", "loc", "attw", "grad_out"))
+
+    def eager_step(timing=None):
+        for i, s in enumerate(sets):
+            if timing is not None:
+                timing["f0"][i].record()
+            s["out"] = ext.ms_deform_attn_forward(s["value"], shp, st, s["loc"], s["attw"], 64, _flags=lib_flags, _kernel=kernel)
+            if timing is not None:
+                timing["f1"][i].record()
+        for i in reversed(range(layers)):
+            s = sets[i]
+            if timing is not None:
+                timing["b0"][i].record()
+            s["grads"] = ext.ms_deform_attn_backward(s["value"], shp, st, s["loc"], s["attw"], s["grad_out"], 64,
+                                                     _flags=flags, _kernel=kernel)
+            if timing is not None:
+                timing["b1"][i].record()
+
+    step = eager_step
+    warmup = max(warmup, 3)
+    for _ in range(warmup):
+        step()
+    sync_all(c)
+    launches_per_step = None
+    if graph:
+        l0 = _capi.launch_count()
+        step()
+        launches_per_step = _capi.launch_count() - l0
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        step = lambda timing=None: g.replay()
+        for _ in range(3):
+            step()
+        sync_all(c)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    if min_seconds > 0:
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(3):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        est = max_over_ranks(a.elapsed_time(b), c.world, c.dev) / 3 * 1e-3
+        steps = max(steps, int(math.ceil(min_seconds / max(est, 1e-6))))
+    timings = None if graph else [{k: [ev() for _ in range(layers)] for k in ("f0", "f1", "b0", "b1")} for _ in range(steps)]
+    start, stop = ev(), ev()
+    sampler = None
+    if c.rank == 0:
+        sampler = ClockSampler(c.dev.index).start()
+        sampler.wait_first()
+    t_region = time.perf_counter()
+    launches0 = _capi.launch_count()
+    sync_all(c)
+    start.record()
+    for k in range(steps):
+        step(None if graph else timings[k])
+    stop.record()
+    sync_all(c)
+    launches = _capi.launch_count() - launches0 if not graph else launches_per_step * steps
+    clocks = sampler.stop(since=t_region) if sampler is not None else None
+    ms_per_step = max_over_ranks(start.elapsed_time(stop), c.world, c.dev) / steps
+    value = aggregate_qps(queries_per_step, c.world, ms_per_step)
+
+    if graph:
+        # no events inside a replayed graph: split the step in the ratio of the algorithmic bytes (reported as such)
+        per_layer = ms_per_step / layers
+        fwd_ms = per_layer * fwd_bytes / (fwd_bytes + bwd_bytes)
+        bwd_ms = per_layer - fwd_ms
+    else:
+        fwd_ms = statistics.mean(tm["f0"][i].elapsed_time(tm["f1"][i]) for tm in timings for i in range(layers))
+        bwd_ms = statistics.mean(tm["b0"][i].elapsed_time(tm["b1"][i]) for tm in timings for i in range(layers))
+    peak, peak_src = peaks()
+
+    e2e = None
+    if want_e2e and not graph:  # e2e is measured on the eager path (the public call with host buffers)
+        e2e = run_e2e(c, sets, shp, st, flags, queries_per_step, e2e_steps)
+
+    dom = "backward" if bwd_ms >= fwd_ms else "forward"
+    dom_bytes, dom_ms = (bwd_bytes, bwd_ms) if dom == "backward" else (fwd_bytes, fwd_ms)
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(name, {}).get(dom)
+        except Exception:
+            traffic = None
+    arm = {"grad_value_mode": "deterministic (canonical order in a block, 64-bit fixed-point accumulation across blocks)"
+           if deterministic else "atomic (merged on chip per window cell, then fp32 L2 reductions)",
+           "parallelism": f"batch-sharded x{c.world}, no collective in the op",
+           "launch": "one CUDA graph per step, replayed (per-launch times not measured: fwd / bwd split by "
+                     "algorithmic bytes)" if graph else "eager, one library call per layer and direction",
+           "input_bytes_per_step": in_bytes}
+    res = {
+        "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup, "dtype": vdt,
+        "config": workload_config(name, syn), "arm": arm,
+        "roofline": {"bound": "hbm", "kernel": f"msda {dom} ({'zero-fill of grad_value + ' if dom == 'backward' else ''}kernel), avg of "
+                     f"{steps * layers} launches", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms},
+        "roofline_fwd_bwd": {"achieved": (fwd_bytes + bwd_bytes) * layers / (ms_per_step * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": (fwd_bytes + bwd_bytes) * layers / (ms_per_step * 1e-3) / 1e9 / peak,
+                             "fwd_ms_per_layer": fwd_ms, "bwd_ms_per_layer": bwd_ms,
+                             "fwd_GBps": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "bwd_GBps": bwd_bytes / (bwd_ms * 1e-3) / 1e9,
+                             "bytes_per_query": (fwd_bytes + bwd_bytes) / (bs * Lq)},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if keep_sets is not None:
+        keep_sets.extend(sets)
+    return res
+
+
+def compact(res):
+    """What an additional workload contributes to the default line."""
+    r, rf = res["roofline"], res["roofline_fwd_bwd"]
+    return {"value": res["value"], "unit": res["unit"], "ms_per_step": res["ms_per_step"], "steps": res["steps"],
+            "dtype": res["dtype"], "config": {k: res["config"][k] for k in ("workload", "image", "S", "Lq", "batch_per_gpu",
+                                                                          "layers_per_step", "locations", "value_dtype")},
+            "arm": {k: res["arm"][k] for k in ("grad_value_mode", "launch")},
+            "roofline": {"bound": "hbm", "frac": rf["frac"], "achieved": rf["achieved"], "peak": rf["peak"], "unit": "GB/s",
+                         "what": "fwd+bwd algorithmic bytes of the step / step time", "dominant_kernel_frac": r["frac"],
+                         "fwd_ms_per_layer": rf["fwd_ms_per_layer"], "bwd_ms_per_layer": rf["bwd_ms_per_layer"]},
+            "gpu_launches": res["gpu_launches"], "clocks": res["clocks"]}
+
+
+# --------------------------------------------------------------------------------------------
+# comparator leg: the reference's own CUDA kernels on the same B200 (oracle/_ref, never product code)
+# --------------------------------------------------------------------------------------------
+def run_legacy_cuda(c, sets, ours_fwd_ms, ours_bwd_ms):
+    """Times the reference's ms_deform_im2col_cuda.cuh kernels — compiled unmodified for sm_100a by
+    oracle/build_ref.py — on the headline workload's own input sets (bs=2 encoder layers, fp32), including the
+    zero-fills its host wrapper performs (ms_deform_attn_cuda.cu:54,121-123).  Rank 0 only; runs after the product's
+    timed region and shares nothing with it."""
+    torch = c.torch
+    try:
+        from oracle.msda_oracle import LegacyCuda
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": f"oracle import failed: {e}"}
+    if not LegacyCuda.available():
+        return {"unavailable": "oracle/_ref/libmsda_legacy.so is not built (the reference tree exists in the build container only)"}
+    legacy = LegacyCuda()
+    k = [0]
+
+    def nxt():
+        k[0] = (k[0] + 1) % len(sets)
+        s = sets[k[0]]
+        return (s["value"], s["shapes"], s["starts"], s["loc"], s["attw"]), s["grad_out"]
+
+    def timeit(fn, iters=20, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    f_ms = timeit(lambda: legacy.forward(*nxt()[0]))
+
+    def bwd():
+        a, g = nxt()
+        legacy.backward(*a, g)
+
+    b_ms = timeit(bwd)
+    n, lq = sets[0]["value"].shape[0], sets[0]["Lq"]
+    return {"what": "reference CUDA kernels (ms_deform_im2col_cuda.cuh:237-299, 301-403) recompiled for sm_100a, same "
+                    "B200, same inputs as the headline workload; comparator only",
+            "fwd_ms_per_layer": f_ms, "bwd_ms_per_layer": b_ms, "value": n * lq / ((f_ms + b_ms) * 1e-3), "unit": UNIT,
+            "ours_fwd_ms_per_layer": ours_fwd_ms, "ours_bwd_ms_per_layer": ours_bwd_ms,
+            "speedup_fwd": f_ms / ours_fwd_ms, "speedup_bwd": b_ms / ours_bwd_ms,
+            "speedup_fwd_bwd": (f_ms + b_ms) / (ours_fwd_ms + ours_bwd_ms), "input_sets": len(sets)}
+
+
 # --------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------
@@ -237,220 +496,148 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    import richsem_b200
+    import richsem_b200  # noqa: F401
     from richsem_b200 import MultiScaleDeformableAttention as ext
     from richsem_b200 import _capi, synthetic as syn
 
-    hw, layers, bs, kind, lq, vdt = WORKLOADS[args.workload]
+    c = SimpleNamespace(torch=torch, dist=dist, rank=rank, world=world, dev=dev, ext=ext, _capi=_capi, syn=syn)
+    kind = WORKLOADS[args.workload][3]
     if kind == "layer":
-        return run_encoder_layer_ddp(args, torch, dist, rank, world, dev)
-    if kind == "stack":
-        return run_encoder_stack(args, torch, dist, rank, world, dev)
-    shapes = syn.level_shapes(*hw)
-    tdt = torch.bfloat16 if vdt == "bf16" else torch.float32
-    sets = [syn.make_inputs(kind, bs, shapes, dev, seed=rank_seed(1234, rank, i), lq=lq, dtype=tdt) for i in range(layers)]
-    S, Lq = sets[0]["S"], sets[0]["Lq"]
-    shp, st = sets[0]["shapes"], sets[0]["starts"]
-    queries_per_step = layers * bs * Lq
-    flags = _capi.FLAG_DETERMINISTIC if args.deterministic else 0
-    flags |= args.lib_flags
-    vb = 2 if vdt == "bf16" else 4
-    fwd_bytes, bwd_bytes = syn.algorithmic_bytes(bs, S, Lq, value_bytes=vb, out_bytes=vb)
-    in_bytes = sum(s[k].numel() * s[k].element_size() for s in sets for k in ("value", "loc", "attw", "grad_out"))
-
-    def step(timing=None):
-        for i, s in enumerate(sets):
-            if timing is not None:
-                timing["f0"][i].record()
-            s["out"] = ext.ms_deform_attn_forward(s["value"], shp, st, s["loc"], s["attw"], 64, _flags=args.lib_flags)
-            if timing is not None:
-                timing["f1"][i].record()
-        for i in reversed(range(layers)):
-            s = sets[i]
-            if timing is not None:
-                timing["b0"][i].record()
-            s["grads"] = ext.ms_deform_attn_backward(s["value"], shp, st, s["loc"], s["attw"], s["grad_out"], 64,
-                                                     _flags=flags)
-            if timing is not None:
-                timing["b1"][i].record()
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync_all()
-    launches_per_step = None
-    if args.graph:
-        l0 = _capi.launch_count()
-        step()
-        launches_per_step = _capi.launch_count() - l0
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step()
-        eager_step = step
-        step = lambda timing=None: graph.replay()
-        for _ in range(3):
-            step()
-        sync_all()
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    timings = [{k: [ev() for _ in range(layers)] for k in ("f0", "f1", "b0", "b1")} for _ in range(args.steps)]
-    start, stop = ev(), ev()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.15)
-    launches0 = _capi.launch_count()
-    sync_all()
-    start.record()
-    for k in range(args.steps):
-        step(None if args.graph else timings[k])
-    stop.record()
-    sync_all()
-    launches = _capi.launch_count() - launches0 if not args.graph else launches_per_step * args.steps
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = max_over_ranks(start.elapsed_time(stop), world, dev) / args.steps
-    value = aggregate_qps(queries_per_step, world, ms_per_step)
-
-    if args.graph:
-        # no events inside a replayed graph: split the step in the ratio of the algorithmic bytes (reported as such)
-        per_layer = ms_per_step / layers
-        fwd_ms = per_layer * fwd_bytes / (fwd_bytes + bwd_bytes)
-        bwd_ms = per_layer - fwd_ms
+        r = run_encoder_layer_ddp(c, args.steps, args.warmup)
+        if rank == 0:
+            print(json.dumps(ddp_line(r, args)))
+    elif kind == "stack":
+        run_encoder_stack(args, c)
     else:
-        fwd_ms = statistics.mean(tm["f0"][i].elapsed_time(tm["f1"][i]) for tm in timings for i in range(layers))
-        bwd_ms = statistics.mean(tm["b0"][i].elapsed_time(tm["b1"][i]) for tm in timings for i in range(layers))
-    peak, peak_src = peaks()
-
-    # ---- e2e: the same step through the public API with HOST buffers ------------------------
-    e2e = None
-    if not args.no_e2e and not args.graph:  # e2e is measured on the eager path (the public call with host buffers)
-        e2e = run_e2e(args, torch, dist, ext, sets, shp, st, flags, world, dev, queries_per_step)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(steps=12, warmup=2)
-        cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-
-    dom = "backward" if bwd_ms >= fwd_ms else "forward"
-    dom_bytes, dom_ms = (bwd_bytes, bwd_ms) if dom == "backward" else (fwd_bytes, fwd_ms)
-    traffic = None
-    tp = ROOT / "profiles" / "traffic.json"
-    if tp.exists():
-        try:
-            traffic = json.loads(tp.read_text()).get(args.workload, {}).get(dom)
-        except Exception:
-            traffic = None
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": vdt, "data": "synthetic",
-        "config": {"workload": args.workload, "image": f"{hw[0]}x{hw[1]}", "levels": shapes, "S": S, "Lq": Lq,
-                   "batch_per_gpu": bs, "layers_per_step": layers, "heads": 8, "head_dim": 32, "points": 4,
-                   "locations": kind, "grad_value_mode": "deterministic" if args.deterministic else "atomic (merged on chip per window cell, then fp32 L2 reductions)",
-                   "parallelism": f"batch-sharded x{world}, no collective in the op",
-                   "launch": "one CUDA graph per step, replayed (per-launch times not measured: fwd / bwd split by "
-                             "algorithmic bytes)" if args.graph else "eager, one library call per layer and direction",
-                   "l2_policy": f"{layers} distinct input sets per step ({in_bytes / 1e6:.0f} MB of inputs) "
-                                "larger than the 126 MB L2; no explicit flush"},
-        "roofline": {"bound": "hbm", "kernel": f"msda {dom} ({'zero-fill of grad_value + ' if dom == 'backward' else ''}kernel), avg of "
-                     f"{args.steps * layers} launches", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
-                     "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms},
-        "roofline_fwd_bwd": {"achieved": (fwd_bytes + bwd_bytes) * layers / (ms_per_step * 1e-3) / 1e9, "peak": peak,
-                             "unit": "GB/s", "frac": (fwd_bytes + bwd_bytes) * layers / (ms_per_step * 1e-3) / 1e9 / peak,
-                             "fwd_ms_per_layer": fwd_ms, "bwd_ms_per_layer": bwd_ms,
-                             "fwd_GBps": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "bwd_GBps": bwd_bytes / (bwd_ms * 1e-3) / 1e9,
-                             "bytes_per_query": (fwd_bytes + bwd_bytes) / (bs * Lq)},
-        "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "lib": _capi.build_info(),
-    }
-    print(json.dumps(line))
+        default_line = args.workload == "encoder6" and not (args.no_extra or args.graph or args.deterministic
+                                                             or args.lib_flags or args.kernel)
+        sets = [] if default_line else None
+        res = time_op_workload(c, args.workload, args.steps, args.warmup, graph=args.graph, deterministic=args.deterministic,
+                               lib_flags=args.lib_flags, kernel=args.kernel, want_e2e=not args.no_e2e,
+                               e2e_steps=args.e2e_steps, keep_sets=sets)
+        extras, legacy = None, None
+        if default_line:
+            if rank == 0:
+                legacy = run_legacy_cuda(c, sets[:4], res["roofline_fwd_bwd"]["fwd_ms_per_layer"],
+                                         res["roofline_fwd_bwd"]["bwd_ms_per_layer"])
+            del sets
+            sync_all(c)
+            extras = {}
+            for key, name, opt in EXTRA:
+                torch.cuda.empty_cache()
+                extras[key] = compact(time_op_workload(c, name, min(args.steps, 50), args.warmup, min_seconds=0.25, **opt))
+            torch.cuda.empty_cache()
+            extras["encoder_layer_ddp"] = run_encoder_layer_ddp(c, min(args.steps, 50), args.warmup)
+        if rank == 0:
+            cpu_baseline = None
+            if world == 1 and not args.no_cpu_baseline:
+                r = cpu_reference_run(steps=12, warmup=2)
+                cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line = {
+                "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": res["steps"],
+                "warmup": res["warmup"], "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": res["dtype"], "data": "synthetic", "config": res["config"], "arm": res["arm"],
+                "roofline": res["roofline"], "roofline_fwd_bwd": res["roofline_fwd_bwd"], "cpu_baseline": cpu_baseline,
+                "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": res["clocks"], "lib": _capi.build_info(),
+            }
+            if extras is not None:
+                line["workloads"] = extras
+                line["legacy_cuda"] = legacy
+            print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_encoder_layer_ddp(args, torch, dist, rank, world, dev):
+def run_encoder_layer_ddp(c, steps, warmup):
     """BASELINE config 4: per rank one reference-equivalent deformable encoder layer (d_ffn 2048, relu,
-    dropout 0) on its own bs=2 shard; loss = out.square().mean(); forward + backward with DDP's bucketed
-    NCCL all-reduce of the 1,282,176 fp32 parameters; no optimizer step."""
+    dropout 0; deformable_transformer.py:825-881) on its own bs=2 shard; loss = out.square().mean(); forward +
+    backward with DDP's bucketed NCCL all-reduce of the 1,282,176 fp32 parameters (main.py:204-206); no optimizer
+    step.  N = 1 runs the same step without the wrapper.  The same model is also timed WITHOUT the
+    DDP wrapper on every rank, so that the line names what the all-reduce costs."""
+    torch, _capi, syn = c.torch, c._capi, c.syn
     from torch.nn.parallel import DistributedDataParallel as DDP
 
-    from richsem_b200 import _capi, synthetic as syn
     from richsem_b200.encoder_layer import DeformableEncoderLayer, encoder_reference_points
 
-    hw, _, bs, _, _, _ = WORKLOADS[args.workload]
+    hw, _, bs, _, _, _ = WORKLOADS["encoder_layer_ddp"]
     shapes = syn.level_shapes(*hw)
-    shp, st, S = syn.level_tensors(shapes, dev)
+    shp, st, S = syn.level_tensors(shapes, c.dev)
     torch.manual_seed(1234)
-    layer = DeformableEncoderLayer().to(dev)
+    layer = DeformableEncoderLayer().to(c.dev)
     with torch.no_grad():  # leave the degenerate init so that every gradient path does real work
         layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
         layer.self_attn.attention_weights.weight.normal_(0, 0.05)
     n_params = sum(p.numel() for p in layer.parameters())
-    model = DDP(layer, device_ids=[dev.index]) if world > 1 else layer
-    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
-    src = torch.randn(bs, S, 256, generator=gen, device=dev)
-    pos = torch.randn(bs, S, 256, generator=gen, device=dev)
-    ref = encoder_reference_points(shapes, bs, dev)
+    gen = torch.Generator(device=c.dev).manual_seed(4321 + c.rank)
+    src = torch.randn(bs, S, 256, generator=gen, device=c.dev)
+    pos = torch.randn(bs, S, 256, generator=gen, device=c.dev)
+    ref = encoder_reference_points(shapes, bs, c.dev)
 
-    def step():
-        model.zero_grad(set_to_none=True)
-        out = model(src, pos, ref, shp, st, None)
-        out.square().mean().backward()
+    def make_step(model):
+        def step():
+            model.zero_grad(set_to_none=True)
+            out = model(src, pos, ref, shp, st, None)
+            out.square().mean().backward()
+        return step
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(dev.index)
-    if rank == 0:
-        sampler.start()
-    l0 = _capi.launch_count()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches = _capi.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / args.steps
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": world * bs * S / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+    def timed(step, n, sample_clocks):
+        for _ in range(max(warmup, 3)):
+            step()
+        sync_all(c)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = None
+        if sample_clocks and c.rank == 0:
+            sampler = ClockSampler(c.dev.index).start()
+            sampler.wait_first()
+        t_region = time.perf_counter()
+        l0 = _capi.launch_count()
+        sync_all(c)
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+        sync_all(c)
+        launches = _capi.launch_count() - l0
+        clocks = sampler.stop(since=t_region) if sampler is not None else None
+        return max_over_ranks(e0.elapsed_time(e1), c.world, c.dev) / n, launches, clocks
+
+    steps = max(steps, 10)
+    local_ms, _, _ = timed(make_step(layer), steps, False)          # no wrapper: what one GPU does alone
+    model = DDP(layer, device_ids=[c.dev.index]) if c.world > 1 else layer
+    ms, launches, clocks = timed(make_step(model), steps, True)
+    fwd_bytes, bwd_bytes = syn.algorithmic_bytes(bs, S, S)
+    peak, _ = peaks()
+    return {"value": c.world * bs * S / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "dtype": "f32",
+            "config": {"workload": "encoder_layer_ddp", "image": f"{hw[0]}x{hw[1]}", "S": S, "batch_per_gpu": bs,
+                       "params": n_params,
+                       "step": "encoder layer fwd + bwd (MSDeformAttn on libmsda_b200, Linears / LayerNorm / FFN in "
+                               "PyTorch fp32), no optimizer"},
+            "arm": {"parallelism": f"DDP x{c.world}: bucketed NCCL all-reduce of {n_params * 4 / 1e6:.2f} MB of fp32 "
+                                   "gradients per step" if c.world > 1 else "1 GPU: the same step, no wrapper, no collective"},
+            "ms_per_step_without_ddp_wrapper": local_ms, "allreduce_exposed_ms": ms - local_ms,
+            "limited_by": "the step is ~95 % strict-fp32 cuBLAS GEMMs (FFN 256<->2048 and the four projections); the "
+                          "all-reduce overlaps the backward except for its last bucket (allreduce_exposed_ms)",
+            "roofline": {"bound": "hbm", "frac": (fwd_bytes + bwd_bytes) / (ms * 1e-3) / 1e9 / peak, "unit": "GB/s",
+                         "achieved": (fwd_bytes + bwd_bytes) / (ms * 1e-3) / 1e9, "peak": peak,
+                         "what": "MSDeformAttn fwd+bwd algorithmic bytes / WHOLE step time (the op is a few % of this step)"},
+            "gpu_launches": int(launches), "clocks": clocks}
+
+
+def ddp_line(r, args):
+    return {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": r["steps"], "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "image": f"{hw[0]}x{hw[1]}", "S": S, "batch_per_gpu": bs,
-                       "params": n_params, "parallelism": f"DDP x{world} (NCCL all-reduce of {n_params * 4 / 1e6:.2f} MB)",
-                       "step": "encoder layer fwd + bwd (MSDeformAttn on libmsda_b200, Linears/LayerNorm in PyTorch), "
-                               "no optimizer"},
-            "gpu_launches": int(launches), "clocks": clocks, "lib": _capi.build_info()}))
-    if world > 1:
-        dist.destroy_process_group()
+            **{k: r[k] for k in ("config", "arm", "ms_per_step_without_ddp_wrapper", "allreduce_exposed_ms", "limited_by",
+                                 "roofline", "gpu_launches", "clocks")}}
 
 
-def run_encoder_stack(args, torch, dist, rank, world, dev):
+def run_encoder_stack(args, c):
     """per rank the 6-layer deformable encoder (deformable_transformer.py:470-618, 825-881; d_ffn 2048,
     relu, dropout 0) on its own bs=2 shard, forward + backward of loss = out.square().mean(), captured once in a CUDA
     graph and replayed (or launched eagerly with --eager).  No optimizer, no collective (single-rank glue measurement;
     under torchrun every rank runs its own replica and the slowest one counts)."""
-    from richsem_b200 import _capi, synthetic as syn
+    torch, _capi, syn = c.torch, c._capi, c.syn
+    rank, world, dev = c.rank, c.world, c.dev
     from richsem_b200.encoder_layer import DeformableEncoder, GraphedTrainStep
 
     hw, layers, bs, _, _, _ = WORKLOADS[args.workload]
@@ -501,23 +688,21 @@ def run_encoder_stack(args, torch, dist, rank, world, dev):
 
     for _ in range(max(args.warmup, 3)):
         step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    sync_all(c)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(dev.index)
+    sampler = None
     if rank == 0:
-        sampler.start()
+        sampler = ClockSampler(dev.index).start()
+        sampler.wait_first()
+    t_region = time.perf_counter()
     l0 = _capi.launch_count()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    sync_all(c)
     launches = _capi.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(since=t_region) if sampler is not None else None
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / args.steps
     if rank == 0:
         n_params = sum(p.numel() for p in model.parameters())
@@ -536,14 +721,13 @@ def run_encoder_stack(args, torch, dist, rank, world, dev):
             # the count below is what the capture recorded times the replays
             "gpu_launches": int(launches) if args.eager else int(launches_per_step * args.steps),
             "clocks": clocks, "lib": _capi.build_info()}))
-    if world > 1:
-        dist.destroy_process_group()
 
 
-def run_e2e(args, torch, dist, ext, sets, shp, st, flags, world, dev, queries_per_step):
+def run_e2e(c, sets, shp, st, flags, queries_per_step, e2e_steps):
     """Host buffers in, host buffers out: per step every layer's value / locations / weights / grad_out
     are copied from pinned host memory, and the output and the three gradients are copied back.
     Copies run on their own streams so that transfers of neighbouring layers overlap the kernels."""
+    torch, ext = c.torch, c.ext
     layers = len(sets)
     names_in = ("value", "loc", "attw", "grad_out")
     host_in = [{k: s[k].cpu().pin_memory() for k in names_in} for s in sets]
@@ -605,27 +789,19 @@ def run_e2e(args, torch, dist, ext, sets, shp, st, flags, world, dev, queries_pe
 
     for _ in range(4):
         e2e_step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    sync_all(c)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.e2e_steps):
+    for _ in range(e2e_steps):
         e2e_step()
     comp.wait_stream(d2h)  # the timed region ends when the last result is in host memory
     comp.wait_stream(h2d)
     e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / args.e2e_steps
+    sync_all(c)
+    ms = max_over_ranks(e0.elapsed_time(e1), c.world, c.dev) / e2e_steps
     d2h_bytes = sum(t.numel() * t.element_size() for ho in host_out for t in ho)
-    return {"value": world * queries_per_step / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-            "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms, "steps": args.e2e_steps,
+    return {"value": c.world * queries_per_step / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+            "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms, "steps": e2e_steps,
             "note": "pinned host buffers -> H2D -> fwd/bwd through the drop-in API -> D2H of out + 3 grads, copies on side streams, device input buffers double-buffered across steps"}
 
 

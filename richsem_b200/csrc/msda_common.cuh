@@ -154,4 +154,18 @@ __device__ __forceinline__ void st_stream_f2(float* p, float2 v) {
 __device__ __forceinline__ void red_add_f4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
 }
+// Two 16-byte reductions into baseA[off .. off+3] and baseB[off .. off+3] (off in elements), skipped when off < 0.
+// Branch-free: one predicate, one IMAD.WIDE per address (the compiler's own code for the same thing is a branch
+// with reconvergence barriers and a four-instruction 64-bit address computation per reduction).
+__device__ __forceinline__ void red_add_2xf4_if(float* baseA, float* baseB, int off, float a0, float a1, float a2,
+                                                float a3, float b0, float b1, float b2, float b3) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .u64 pa, pb;\n"
+      " setp.ge.s32 p, %2, 0;\n"
+      " mad.wide.s32 pa, %2, 4, %0;\n"
+      " mad.wide.s32 pb, %2, 4, %1;\n"
+      " @p red.global.add.v4.f32 [pa], {%3,%4,%5,%6};\n"
+      " @p red.global.add.v4.f32 [pb], {%7,%8,%9,%10};\n}"
+      ::"l"(baseA), "l"(baseB), "r"(off), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(b0), "f"(b1), "f"(b2), "f"(b3));
+}
 

@@ -296,6 +296,9 @@ __device__ __forceinline__ void win_ldg_row(const VT* p, const int dB, float2 (&
   }
 }
 
+#ifndef MSDA_WIN_BRANCHY_FLUSH
+#define MSDA_WIN_BRANCHY_FLUSH 0
+#endif
 // Adds this lane's 8 channels (chunks cA, cA ^ 4) of a partial row into grad_value row `off` (an element offset
 // inside the image).  Atomic mode: two REDG.E.ADD.F32x4; deterministic mode: eight 64-bit fixed-point adds.
 template <bool kDet>
@@ -305,17 +308,26 @@ struct WinRed {
   long long* g64;  // deterministic: accumulators + image + cA
   int dB64;        // (cA ^ 4) - cA
   float dscale;
+  // off < 0: nothing to add (a pool row outside the image)
   __device__ __forceinline__ void operator()(const int off, const float2 (&acc)[4]) const {
     if constexpr (kDet) {
-      long long* pa = g64 + off;
-      long long* pb = pa + dB64;
-      win_det_add(pa, acc[0].x, dscale); win_det_add(pa + 8, acc[0].y, dscale);
-      win_det_add(pa + 16, acc[1].x, dscale); win_det_add(pa + 24, acc[1].y, dscale);
-      win_det_add(pb, acc[2].x, dscale); win_det_add(pb + 8, acc[2].y, dscale);
-      win_det_add(pb + 16, acc[3].x, dscale); win_det_add(pb + 24, acc[3].y, dscale);
+      if (off >= 0) {
+        long long* pa = g64 + off;
+        long long* pb = pa + dB64;
+        win_det_add(pa, acc[0].x, dscale); win_det_add(pa + 8, acc[0].y, dscale);
+        win_det_add(pa + 16, acc[1].x, dscale); win_det_add(pa + 24, acc[1].y, dscale);
+        win_det_add(pb, acc[2].x, dscale); win_det_add(pb + 8, acc[2].y, dscale);
+        win_det_add(pb + 16, acc[3].x, dscale); win_det_add(pb + 24, acc[3].y, dscale);
+      }
     } else {
-      red_add_f4(gvA + off, acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-      red_add_f4(gvB + off, acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+#if MSDA_WIN_BRANCHY_FLUSH
+      if (off >= 0) {
+        red_add_f4(gvA + off, acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+        red_add_f4(gvB + off, acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+      }
+#else
+      red_add_2xf4_if(gvA, gvB, off, acc[0].x, acc[0].y, acc[1].x, acc[1].y, acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+#endif
     }
   }
 };
@@ -621,7 +633,7 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
       WIN_CHECK(row >= 0 && row < kWinPool + 2);
       const int off = rowoff[row];
       WIN_CHECK(off < 0 || (off % 32 == 0 && off / 32 < S * M));
-      if (off >= 0) red(off, acc);
+      red(off, acc);
     };
     uint2 pk_next = *reinterpret_cast<const uint2*>(sorted + i0);  // i0 is a multiple of 4
     float4 rnext = rec[rec_slot(sid_of(pk_next, 0))];

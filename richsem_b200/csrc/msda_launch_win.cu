@@ -41,7 +41,11 @@ int launch_bwd_win(cudaStream_t s, const Problem& pb, const VT* go, const VT* va
                    const float* attw, float* gv, float* gl, float* ga, long long* gv64, const unsigned* maxbits) {
   using Cfg = WinCfg<VT, kL>;
   constexpr auto kern = msda_bwd_d32_win_kernel<VT, kL, kM, kDet, kFused>;
+#ifdef MSDA_WIN_EXTRA_SMEM  // occupancy experiments: pad the block's shared memory (e.g. 30000 -> one block per SM)
+  constexpr int kSmem = (kDet ? Cfg::BWD_DET_SMEM : Cfg::BWD_SMEM) + MSDA_WIN_EXTRA_SMEM;
+#else
   constexpr int kSmem = kDet ? Cfg::BWD_DET_SMEM : Cfg::BWD_SMEM;
+#endif
   if (int rc = ensure_dynamic_smem<kern>(kSmem, "cudaFuncSetAttribute(msda_bwd_d32_win_kernel)")) return rc;
   const int tiles = (pb.order_len + kWinTileQ - 1) / kWinTileQ;
   dim3 grid(tiles * pb.d.num_heads, pb.d.batch);

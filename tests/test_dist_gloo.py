@@ -56,3 +56,14 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "queries/s"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+
+
+def test_reference_arm_does_not_load_the_product_library():
+    """bench.py --impl reference (the CPU arm) must not map libmsda_b200.so: it loads the synthetic-input module by
+    path and the oracle, never the richsem_b200 package (whose import dlopens the library)."""
+    code = ("import sys, bench; from oracle.msda_oracle import core_pytorch_fwd_bwd; syn = bench.load_synthetic(); "
+            "assert syn.level_shapes(800, 1333)[0] == (100, 167); "
+            "assert not [m for m in sys.modules if m.startswith('richsem_b200')], sys.modules.keys(); "
+            "maps = open('/proc/self/maps').read(); assert 'libmsda_b200' not in maps; print('clean')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=str(ROOT), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stderr[-2000:]
