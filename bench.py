@@ -350,7 +350,17 @@ def time_op_workload(c, name, steps, warmup, graph=False, deterministic=False, l
         torch.cuda.synchronize()
         est = max_over_ranks(a.elapsed_time(b), c.world, c.dev) / 3 * 1e-3
         steps = max(steps, int(math.ceil(min_seconds / max(est, 1e-6))))
-    timings = None if graph else [{k: [ev() for _ in range(layers)] for k in ("f0", "f1", "b0", "b1")} for _ in range(steps)]
+    # Per-layer CUDA events inside the timed region give the fwd / bwd split of every launch — unless the calls are so
+    # short (decoder layers: 14-36 us kernels) that recording four events per layer would itself slow the step down;
+    # those workloads time the plain loop and take the split from a second, instrumented pass.
+    est_probe = (ev(), ev())
+    est_probe[0].record()
+    step()
+    est_probe[1].record()
+    torch.cuda.synchronize()
+    inner_events = not graph and est_probe[0].elapsed_time(est_probe[1]) / (2 * layers) > 0.1
+    mk = lambda n: [{k: [ev() for _ in range(layers)] for k in ("f0", "f1", "b0", "b1")} for _ in range(n)]
+    timings = mk(steps) if inner_events else None
     start, stop = ev(), ev()
     sampler = None
     if c.rank == 0:
@@ -361,7 +371,7 @@ def time_op_workload(c, name, steps, warmup, graph=False, deterministic=False, l
     sync_all(c)
     start.record()
     for k in range(steps):
-        step(None if graph else timings[k])
+        step(timings[k] if inner_events else None)
     stop.record()
     sync_all(c)
     launches = _capi.launch_count() - launches0 if not graph else launches_per_step * steps
@@ -369,14 +379,25 @@ def time_op_workload(c, name, steps, warmup, graph=False, deterministic=False, l
     ms_per_step = max_over_ranks(start.elapsed_time(stop), c.world, c.dev) / steps
     value = aggregate_qps(queries_per_step, c.world, ms_per_step)
 
+    split_note = "CUDA events around every launch inside the timed region"
     if graph:
         # no events inside a replayed graph: split the step in the ratio of the algorithmic bytes (reported as such)
         per_layer = ms_per_step / layers
         fwd_ms = per_layer * fwd_bytes / (fwd_bytes + bwd_bytes)
         bwd_ms = per_layer - fwd_ms
+        split_note = "graph replay: step time split by algorithmic bytes"
     else:
+        if not inner_events:
+            timings = mk(min(steps, 20))
+            for tm in timings:
+                eager_step(tm)
+            torch.cuda.synchronize()
+            split_note = "fwd / bwd ratio from a second, instrumented pass, scaled to the timed region's step time"
         fwd_ms = statistics.mean(tm["f0"][i].elapsed_time(tm["f1"][i]) for tm in timings for i in range(layers))
         bwd_ms = statistics.mean(tm["b0"][i].elapsed_time(tm["b1"][i]) for tm in timings for i in range(layers))
+        if not inner_events:
+            scale = (ms_per_step / layers) / (fwd_ms + bwd_ms)
+            fwd_ms, bwd_ms = fwd_ms * scale, bwd_ms * scale
     peak, peak_src = peaks()
 
     e2e = None
@@ -397,7 +418,7 @@ def time_op_workload(c, name, steps, warmup, graph=False, deterministic=False, l
            "parallelism": f"batch-sharded x{c.world}, no collective in the op",
            "launch": "one CUDA graph per step, replayed (per-launch times not measured: fwd / bwd split by "
                      "algorithmic bytes)" if graph else "eager, one library call per layer and direction",
-           "input_bytes_per_step": in_bytes}
+           "input_bytes_per_step": in_bytes, "fwd_bwd_split": split_note}
     res = {
         "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup, "dtype": vdt,
         "config": workload_config(name, syn), "arm": arm,

@@ -211,11 +211,13 @@ int backward_impl(cudaStream_t s, const TV* grad_out, const TV* value, const int
   return msda::bwd_generic<TV, TA>(s, pb, !no_gv, grad_out, value, loc, attw, gv, gl, ga);
 }
 
-// ---- fused prologue: large D=32 problems only, default kernels only ----------------------
+// ---- fused prologue: head_dim-32 problems served by the window (encoder self-attention) or the split
+// (decoder cross-attention) family ----------------------------------------------------------------------------------
 bool fused_supported(const Problem& pb, int dtype_bytes) {
   const uint32_t bad = MSDA_FLAG_DETERMINISTIC | MSDA_FLAG_FORCE_GENERIC | MSDA_FLAG_NO_GRAD_VALUE;
+  const int fam = msda::kernel_family(pb);
   return !(pb.flags & bad) && fast_shape(dtype_bytes, pb.d.channels, pb.d.num_levels, pb.d.num_point) &&
-         fits_int32(pb.d) && msda::kernel_family(pb) == MSDA_KERNEL_WINDOW && pb.d.batch > 0 && pb.d.num_query > 0;
+         fits_int32(pb.d) && (fam == MSDA_KERNEL_WINDOW || fam == MSDA_KERNEL_SPLIT) && pb.d.batch > 0 && pb.d.num_query > 0;
 }
 
 template <typename TV>
@@ -229,7 +231,8 @@ int forward_fused_impl(cudaStream_t s, const TV* value, const int64_t* shapes, c
   int rc = make_problem(s, shapes, start, batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, opts, &pb);
   if (rc != MSDA_OK) return rc;
   if (!fused_supported(pb, sizeof(TV)) || !aligned(value, 16) || !aligned(offsets, 16) || !aligned(logits, 16) || !aligned(out, 16))
-    return fail(MSDA_ERR_UNSUPPORTED, "no fused-prologue kernel for this problem (needs a large D=32, P=4 problem and default flags)");
+    return fail(MSDA_ERR_UNSUPPORTED, "no fused-prologue kernel for this problem (needs head_dim 32, 4 points, 3-5 levels, the "
+                                      "window or split kernel family and default flags)");
   pb.fz = MsdaFused{ref, ref_dim};
   return msda::fwd_d32<TV>(s, pb, value, offsets, logits, out);
 }
@@ -247,13 +250,24 @@ int backward_fused_impl(cudaStream_t s, const TV* grad_out, const TV* value, con
   if (rc != MSDA_OK) return rc;
   if (!fused_supported(pb, sizeof(TV)) || !aligned(value, 16) || !aligned(gv, 16) || !aligned(offsets, 16) ||
       !aligned(logits, 16) || !aligned(grad_out, 16) || !aligned(g_offsets, 16) || !aligned(g_logits, 16))
-    return fail(MSDA_ERR_UNSUPPORTED, "no fused-prologue kernel for this problem (needs a large D=32, P=4 problem and default flags)");
+    return fail(MSDA_ERR_UNSUPPORTED, "no fused-prologue kernel for this problem (needs head_dim 32, 4 points, 3-5 levels, the "
+                                      "window or split kernel family and default flags)");
   pb.fz = MsdaFused{ref, ref_dim};
   if (!(pb.flags & MSDA_FLAG_GRAD_VALUE_PREZEROED)) {
+    // the library's own fill kernel, which the backward kernel is launched behind programmatically: its front end /
+    // gather phase overlaps the fill (see backward_impl)
+    static const bool no_pdl = getenv("MSDA_B200_NO_PDL") && atoi(getenv("MSDA_B200_NO_PDL")) != 0;
     const size_t gv_bytes = (size_t)batch * spatial_size * num_heads * channels * sizeof(float);
-    if ((rc = check_cuda(cudaMemsetAsync(gv, 0, gv_bytes, s), "zero-fill of grad_value"))) return rc;
+    if (!no_pdl) {
+      if ((rc = msda::zero_fill_pdl(s, gv, gv_bytes))) return rc;
+      pb.pdl_after_fill = true;
+    } else if ((rc = check_cuda(cudaMemsetAsync(gv, 0, gv_bytes, s), "zero-fill of grad_value"))) {
+      return rc;
+    }
   }
-  return msda::bwd_d32_win<TV>(s, pb, grad_out, value, offsets, logits, gv, g_offsets, g_logits);
+  return msda::kernel_family(pb) == MSDA_KERNEL_WINDOW
+             ? msda::bwd_d32_win<TV>(s, pb, grad_out, value, offsets, logits, gv, g_offsets, g_logits)
+             : msda::bwd_d32<TV, true>(s, pb, grad_out, value, offsets, logits, gv, g_offsets, g_logits);
 }
 
 }  // namespace

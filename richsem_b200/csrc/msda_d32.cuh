@@ -150,7 +150,7 @@ __device__ __forceinline__ void d32_decode_points(const float* __restrict__ loc,
                                                   const int j, const int m, const int M,
                                                   const MsdaLevels& lv, float4* rec,
                                                   const MsdaFused fz = MsdaFused{nullptr, 0}, const size_t bq = 0,
-                                                  const unsigned gmask = 0xffffffffu) {
+                                                  const unsigned gmask = 0xffffffffu, float* first_weight = nullptr) {
   constexpr int LP = kL * kP, KPTS = (LP + G - 1) / G;
   float2 xy[KPTS];
   float a[KPTS];
@@ -187,6 +187,7 @@ __device__ __forceinline__ void d32_decode_points(const float* __restrict__ loc,
       if (p < LP) xy[k] = msda_fused_location(fz, bq, kL, p / kP, kP, lv.H[p / kP], lv.W[p / kP], xy[k]);
     }
   }
+  if (first_weight) *first_weight = a[0];  // weight of point j (after the softmax, if fused)
 #pragma unroll
   for (int k = 0; k < KPTS; ++k) {
     const int p = j + G * k;
@@ -449,7 +450,8 @@ template <typename VT, int kL, int kP, int kM>
 __global__ void __launch_bounds__(kSplitThreads)
 msda_fwd_d32_split_kernel(const VT* __restrict__ value, const float* __restrict__ loc,
                           const float* __restrict__ attw, VT* __restrict__ out,
-                          const __grid_constant__ MsdaLevels lv, const int S, const int M_rt, const int Lq) {
+                          const __grid_constant__ MsdaLevels lv, const int S, const int M_rt, const int Lq,
+                          const MsdaFused fz) {
   constexpr int LP = kL * kP;
   using RT = RowTraits<VT>;
   constexpr int G = RT::G, C = RT::C, GPW = 32 / G;
@@ -466,7 +468,7 @@ msda_fwd_d32_split_kernel(const VT* __restrict__ value, const float* __restrict_
   float4* rec = smem + warp * (LP + 1);
   const VT* value_b = value + (size_t)b * S * M32 + j * C;
   const size_t qm = ((size_t)b * Lq + q) * M + m;
-  d32_decode_points<32, kL, kP>(loc, attw, qm, lane, m, M, lv, rec);
+  d32_decode_points<32, kL, kP>(loc, attw, qm, lane, m, M, lv, rec, fz, (size_t)b * Lq + q);
   __syncwarp();
   float acc[C];
 #pragma unroll
@@ -513,12 +515,13 @@ msda_bwd_d32_split_kernel(const VT* __restrict__ grad_out, const VT* __restrict_
                           const float* __restrict__ loc, const float* __restrict__ attw,
                           float* __restrict__ grad_value, float* __restrict__ grad_loc,
                           float* __restrict__ grad_attw, const __grid_constant__ MsdaLevels lv,
-                          const int S, const int M_rt, const int Lq) {
+                          const int S, const int M_rt, const int Lq, const MsdaFused fz) {
   constexpr int LP = kL * kP;
   using RT = RowTraits<VT>;
   constexpr int G = RT::G, C = RT::C, GPW = 32 / G;
   constexpr int NPG = (LP + GPW - 1) / GPW;
   __shared__ float4 smem[(kSplitThreads / 32) * (LP + 1)];
+  __shared__ float4 res_s[(kSplitThreads / 32) * LP];  // fused prologue: (d/dx, d/dy, d/da) of every point of the warp's (query, head)
   const int M = kM ? kM : M_rt;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / G, j = lane % G;
@@ -533,7 +536,10 @@ msda_bwd_d32_split_kernel(const VT* __restrict__ grad_out, const VT* __restrict_
   float* gvalue_img = grad_value + (size_t)b * S * M32;
   using SD = ScatterDeal<VT>;
   const size_t qm = ((size_t)b * Lq + q) * M + m;
-  d32_decode_points<32, kL, kP>(loc, attw, qm, lane, m, M, lv, rec);
+  const bool fused = fz.ref_dim != 0;  // grid-uniform
+  float4* res = res_s + warp * LP;
+  float my_a = 0.f;  // lane p < LP: attention weight of point p
+  d32_decode_points<32, kL, kP>(loc, attw, qm, lane, m, M, lv, rec, fz, (size_t)b * Lq + q, 0xffffffffu, &my_a);
   __syncwarp();
   float go[C], gs[C];
   RT::load_stream(grad_out + qm * 32 + j * C, go);
@@ -575,8 +581,32 @@ msda_bwd_d32_split_kernel(const VT* __restrict__ grad_out, const VT* __restrict_
       gy += __shfl_xor_sync(0xffffffffu, gy, s);
     }
     if (j == 0 && p < LP) {
+      if (fused) {
+        res[p] = make_float4(gx, gy, ga, 0.f);
+      } else {
+        st_stream_f2(grad_loc + (qm * LP + p) * 2, make_float2(gx, gy));
+        st_stream_f1(grad_attw + qm * LP + p, ga);
+      }
+    }
+  }
+  if (fused) {
+    // Fused prologue (ms_deform_attn.py:98-111 backwards): lane p turns point p's gradients with respect to the
+    // sampling location and the attention weight into those of the RAW offset and logit.  Softmax backward:
+    // dL/dlogit_p = a_p * (dL/da_p - sum_k a_k * dL/da_k), the sum over the (query, head)'s L*P points (a skipped
+    // sample has dL/da = 0 but keeps its softmax weight); location: loc = ref + off / (W, H)  |  ref.xy + off / P *
+    // ref.wh * 0.5, divisions and products in autograd's order.  Coalesced stores: 128 + 64 contiguous bytes per warp.
+    __syncwarp();
+    const int p = lane, l = min(p / kP, kL - 1);
+    const float4 r = p < LP ? res[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float dot = p < LP ? my_a * r.z : 0.f;
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, sft);
+    if (p < LP) {
+      const float* rp = fz.ref + (((size_t)b * Lq + q) * kL + l) * fz.ref_dim;
+      const float gx = fz.ref_dim == 2 ? r.x / (float)lv.W[l] : r.x * 0.5f * rp[2] / (float)kP;
+      const float gy = fz.ref_dim == 2 ? r.y / (float)lv.H[l] : r.y * 0.5f * rp[3] / (float)kP;
       st_stream_f2(grad_loc + (qm * LP + p) * 2, make_float2(gx, gy));
-      st_stream_f1(grad_attw + qm * LP + p, ga);
+      st_stream_f1(grad_attw + qm * LP + p, my_a * (r.z - dot));
     }
   }
   if (kScatter) {

@@ -36,7 +36,7 @@ int launch_fwd_split(cudaStream_t s, const Problem& pb, const VT* value, const f
   constexpr int QPB = msda::kSplitThreads / 32;
   dim3 grid(((pb.d.num_query + QPB - 1) / QPB) * pb.d.num_heads, pb.d.batch);
   msda::msda_fwd_d32_split_kernel<VT, kL, 4, kM><<<grid, msda::kSplitThreads, 0, s>>>(
-      value, loc, attw, out, pb.lv, pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
+      value, loc, attw, out, pb.lv, pb.d.spatial_size, pb.d.num_heads, pb.d.num_query, pb.fz);
   return after_launch("msda_fwd_d32_split_kernel");
 }
 template <typename VT, int kL, int kM, bool kScatter>
@@ -58,12 +58,12 @@ int launch_bwd_split(cudaStream_t s, const Problem& pb, const VT* grad_out, cons
     cfg.numAttrs = 1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, msda::msda_bwd_d32_split_kernel<VT, kL, 4, kM, kScatter>, grad_out, value,
                                              loc, attw, gv, gl, ga, pb.lv, pb.d.spatial_size, pb.d.num_heads,
-                                             pb.d.num_query);
+                                             pb.d.num_query, pb.fz);
     if (e != cudaSuccess) return check_cuda(e, "launch of msda_bwd_d32_split_kernel");
     return after_launch("msda_bwd_d32_split_kernel");
   }
   msda::msda_bwd_d32_split_kernel<VT, kL, 4, kM, kScatter><<<grid, msda::kSplitThreads, 0, s>>>(
-      grad_out, value, loc, attw, gv, gl, ga, pb.lv, pb.d.spatial_size, pb.d.num_heads, pb.d.num_query);
+      grad_out, value, loc, attw, gv, gl, ga, pb.lv, pb.d.spatial_size, pb.d.num_heads, pb.d.num_query, pb.fz);
   return after_launch("msda_bwd_d32_split_kernel");
 }
 
@@ -103,8 +103,6 @@ int bwd_d32(cudaStream_t s, const Problem& pb, const VT* go, const VT* value, co
     MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL
   }
-  if (pb.d.num_heads == 8 && pb.d.num_levels == 4)
-    return launch_bwd_d32<VT, 4, 8, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga);
 #define CALL(L) launch_bwd_d32<VT, L, 0, kScatter>(s, pb, go, value, loc, attw, gv, gl, ga)
   MSDA_SWITCH_L(pb.d.num_levels, CALL)
 #undef CALL

@@ -99,8 +99,11 @@ class GraphedTrainStep:
 
     def __init__(self, model, loss_fn, example_args, warmup=3):
         self.model, self.loss_fn = model, loss_fn
-        self.static_args = [a.clone() if isinstance(a, torch.Tensor) and a.is_floating_point() else a
-                            for a in example_args]
+        # Every tensor the kernels read on the device gets a static buffer that __call__ refreshes: floating-point
+        # inputs and bool / uint8 masks.  Integer tensors (spatial_shapes, level_start_index) are different: the
+        # library bakes their VALUES into the captured launches (kernel-parameter constant memory), so they are
+        # captured by identity and __call__ refuses other values.
+        self.static_args = [a.clone() if self._refreshed(a) else a for a in example_args]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -121,10 +124,25 @@ class GraphedTrainStep:
         for p in self.model.parameters():
             p.grad = None
 
+    @staticmethod
+    def _refreshed(a):
+        return isinstance(a, torch.Tensor) and (a.is_floating_point() or a.dtype in (torch.bool, torch.uint8))
+
     def __call__(self, *args):
+        if len(args) != len(self.static_args):
+            raise ValueError(f"expected {len(self.static_args)} arguments, got {len(args)}")
         for dst, src in zip(self.static_args, args):
-            if isinstance(dst, torch.Tensor) and dst.is_floating_point() and src is not dst:
-                dst.copy_(src)
+            if self._refreshed(dst):
+                if not isinstance(src, torch.Tensor) or src.shape != dst.shape or src.dtype != dst.dtype:
+                    raise ValueError("argument does not match the captured tensor's shape / dtype")
+                if src is not dst:
+                    dst.copy_(src)
+            elif isinstance(dst, torch.Tensor):
+                if src is not dst and not (isinstance(src, torch.Tensor) and src.shape == dst.shape and torch.equal(src, dst)):
+                    raise ValueError("integer tensor arguments (level shapes / start indices) are baked into the "
+                                     "captured graph; capture a new GraphedTrainStep for different values")
+            elif (src is None) != (dst is None):
+                raise ValueError("an argument that was None at capture time must stay None (and vice versa)")
         self.graph.replay()
         for p, g in zip(self.params, self.grads):
             p.grad = g
