@@ -554,7 +554,6 @@ msda_bwd_d32_split_kernel(const VT* __restrict__ grad_out, const VT* __restrict_
       const int bm = __float_as_int(r.x);
       const float lh = r.y, lw = r.z, a = r.w;
       const float hh = 1.f - lh, hw = 1.f - lw;
-      const float a_hh = a * hh, a_lh = a * lh;
       const ptrdiff_t o0 = (ptrdiff_t)(bm & ~31);
       const ptrdiff_t o2 = o0 + (ptrdiff_t)(lv.W[l] * M32);
       float d[4] = {0.f, 0.f, 0.f, 0.f};
