@@ -56,6 +56,16 @@ constexpr int kWinPool = MSDA_WIN_POOL;
 #define WIN_CHECK(cond) do { } while (0)
 #endif
 
+#ifdef MSDA_WIN_TIMING
+// Debug builds only (scratch/win_timing.py): SM-clock sums over all blocks.  [w] = sorted pass of warp w, [8 + w] =
+// direct pass of warp w, [16] = front end, [17] = blocks, [20..26] = front-end sections as stamped by thread 0; read
+// and cleared by msda_debug_win_timing().
+__device__ unsigned long long g_win_timing[32];
+#define WIN_STAMP(k) do { if (t == 0) { const long long n_ = clock64(); atomicAdd(&g_win_timing[k], (unsigned long long)(n_ - t_stamp_dbg)); t_stamp_dbg = n_; } } while (0)
+#else
+#define WIN_STAMP(k) do { } while (0)
+#endif
+
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // 16-byte global->shared copy that bypasses L1 and registers; src_bytes = 0 writes zeros.
@@ -372,10 +382,24 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
     const int os = tl * kWinTileQ + k;
     return os < order_len ? (order ? order[os] : os) : -1;
   };
+  // every order entry this thread needs is requested before the first load that depends on one (one L2 round trip
+  // instead of three back to back)
   const int q = tile_query(tile, ql);
+  const int qpf = tile_query(tile + kWinPrefetchTiles, ql);
+  int gq_[2];
+  if constexpr (sizeof(VT) == 4) {
+    gq_[0] = tile_query(tile, t >> 3);
+    gq_[1] = tile_query(tile, (t + kWinThreads) >> 3);
+  } else {
+    gq_[0] = gq_[1] = tile_query(tile, t >> 2);
+  }
   const size_t bq = (size_t)b * Lq + (q >= 0 ? q : 0);
   const size_t qm = bq * M + m;
 
+#ifdef MSDA_WIN_TIMING
+  const long long t_start_dbg = clock64();
+  long long t_stamp_dbg = t_start_dbg;
+#endif
   // ---- phase 0: every global load of the front end goes out first -----------------------------------
   float4 rxy01[NLV], rxy23[NLV], raw[NLV];
 #pragma unroll
@@ -396,19 +420,18 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
       const int i = t + it * kWinThreads, gql = i >> 3, gj = i & 7;
-      const int gq = tile_query(tile, gql);
+      const int gq = gq_[it];
       cp_async16(smem_u32(go_s + gql * 32 + gj * 4),
                  grad_out + (((size_t)b * Lq + (gq >= 0 ? gq : 0)) * M + m) * 32 + gj * 4, gq >= 0 ? 16 : 0);
     }
   } else {
     const int gql = t >> 2, gj = t & 3;
-    const int gq = tile_query(tile, gql);
+    const int gq = gq_[0];
 #pragma unroll
     for (int c = 0; c < 8; ++c) go_reg[c] = 0.f;
     if (gq >= 0) RowTraits<__nv_bfloat16>::load_stream(grad_out + (((size_t)b * Lq + gq) * M + m) * 32 + gj * 8, go_reg);
   }
   {  // a later tile's inputs: HBM -> L2 now, so that its front end sees L2 latency
-    const int qpf = tile_query(tile + kWinPrefetchTiles, ql);
     if (qpf >= 0) {
       const size_t qm_pf = ((size_t)b * Lq + qpf) * M + m;
 #pragma unroll
@@ -437,6 +460,7 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
       reinterpret_cast<uint4*>(wcnt)[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
+  WIN_STAMP(20);  // loads issued, init, barrier
 
   // ---- phase 1: decode, bounding boxes ---------------------------------------------------------------
   WinPoint pts[NLV][4];
@@ -457,6 +481,7 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
     }
   }
   __syncthreads();
+  WIN_STAMP(21);  // decode (waits for the loads), bounding boxes, barrier
 
   // ---- phase 2: windows (cp.async left in flight), records, per-cell counts ---------------------------
   int rank[NLV][4];
@@ -538,6 +563,7 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
     *reinterpret_cast<float4*>(d + 4) = make_float4(go_reg[4], go_reg[5], go_reg[6], go_reg[7]);
   }
   __syncthreads();  // counts complete, records visible
+  WIN_STAMP(22);  // allocation, staging issue, records, counts, barrier
 
   // ---- phase 3: counting sort by cell ---------------------------------------------------------------
   if (kDet) {
@@ -575,6 +601,7 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
     if (t == kWinThreads - 1) misc[16] = run;
     __syncthreads();
   }
+  WIN_STAMP(23);  // scan (two barriers)
   // sample ids to their sorted positions; the list is padded with entries that point at the all-zero rows
 #pragma unroll
   for (int li = 0; li < NLV; ++li) {
@@ -591,8 +618,11 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
     }
   }
   if (t < 8) sorted[misc[16] + t] = (unsigned short)Cfg::PAD_SID;
+  WIN_STAMP(24);  // placement
   cp_async_wait_all();
+  WIN_STAMP(25);  // wait for the windows (thread 0's own copies)
   __syncthreads();  // windows, sorted list, grad_out rows are in shared memory
+  WIN_STAMP(26);  // final barrier of the front end
 
   // the front end writes nothing to global memory; everything from here on may reduce into grad_value, which the
   // preceding kernel on the stream zero-fills when this kernel was allowed to start early (programmatic dependent
@@ -617,6 +647,10 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
   };
   auto rec_slot = [](const int sid) { return sid + sid / LP; };  // query * (LP + 1) + point
 
+#ifdef MSDA_WIN_TIMING
+  long long t_dbg = clock64();
+  if (t == 0) { atomicAdd(&g_win_timing[16], (unsigned long long)(t_dbg - t_start_dbg)); atomicAdd(&g_win_timing[17], 1ull); }
+#endif
   // ---- phase 4: sorted pass ----------------------------------------------------------------------------
   {
     const WinLane<VT> wl(pool, cA);
@@ -717,6 +751,10 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
     flush(cur1 + 1, B1);
   }
 
+#ifdef MSDA_WIN_TIMING
+  __syncwarp();
+  if (lane == 0) { const long long n = clock64(); atomicAdd(&g_win_timing[warp], (unsigned long long)(n - t_dbg)); t_dbg = n; }
+#endif
   // ---- phase 5: direct pass — levels that did not get a window; one 4-lane group per query --------------
   {
     int lbase[kL];
@@ -780,6 +818,10 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
       }
     }
   }
+#ifdef MSDA_WIN_TIMING
+  __syncwarp();
+  if (lane == 0) atomicAdd(&g_win_timing[8 + warp], (unsigned long long)(clock64() - t_dbg));
+#endif
   __syncthreads();  // every sample's gradients are parked in its record slot
 
   // ---- phase 6: write-out: thread <-> (level slot, query) as in the decode -------------------------------

@@ -139,4 +139,15 @@ template int bwd_d32_win<float>(cudaStream_t, const Problem&, const float*, cons
 template int bwd_d32_win<__nv_bfloat16>(cudaStream_t, const Problem&, const __nv_bfloat16*, const __nv_bfloat16*,
                                         const float*, const float*, float*, float*, float*);
 
+#ifdef MSDA_WIN_TIMING
+// debug builds only: copies and clears the phase-timing accumulators
+extern "C" int msda_debug_win_timing(unsigned long long* out32) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out32, g_win_timing, sizeof(unsigned long long) * 32);
+  unsigned long long z[32] = {0};
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_win_timing, z, sizeof(z));
+  return (int)e;
+}
+#endif
+
 }  // namespace msda
