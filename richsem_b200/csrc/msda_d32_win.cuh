@@ -41,10 +41,23 @@ namespace msda {
 
 constexpr int kWinTileQ = 64;                 // queries per block; 4 threads per query (one per level slot)
 constexpr int kWinThreads = 4 * kWinTileQ;
-// Rows of the window pool: 448 rows = 57 KB (fp32), two blocks per SM with the sort structures
-// (measured per bs=2 encoder layer, round 1: 256 rows 0.464 ms, 320 0.442, 384 0.425, 448 0.414, 592 0.434).
+// Lanes per lane group of the sorted and direct passes (the group covers the 32 channels of a row):
+//   4 lanes x 8 channels: value rows + accumulators = 64 registers per thread -> 128 registers, two blocks per SM,
+//                         448-row pool (57 KB fp32);
+//   8 lanes x 4 channels: 32 registers of rows + accumulators -> <= 85 registers, THREE blocks per SM with a
+//                         320-row pool (41 KB): the per-sample scalar work is replicated over twice the lanes, but
+//                         the kernel is bound by latency at 16 resident warps (profiles/r2_*), and 24 hide more of it.
+#ifndef MSDA_WIN_G
+#define MSDA_WIN_G 4
+#endif
+constexpr int kWinG = MSDA_WIN_G;
+static_assert(kWinG == 4 || kWinG == 8, "lane groups of 4 or 8 lanes");
+constexpr int kWinNC2 = 16 / kWinG;   // float2 (channel pairs) of a row held by one lane: 4 | 2
+constexpr int kWinNCH = 8 / kWinG;    // 16-byte fp32 chunks of a row held by one lane: 2 | 1
+// Rows of the window pool (measured per bs=2 encoder layer, round 1, 4-lane groups: 256 rows 0.464 ms, 320 0.442,
+// 384 0.425, 448 0.414, 592 0.434).
 #ifndef MSDA_WIN_POOL
-#define MSDA_WIN_POOL 448
+#define MSDA_WIN_POOL (MSDA_WIN_G == 4 ? 448 : 320)
 #endif
 constexpr int kWinPool = MSDA_WIN_POOL;
 
@@ -259,58 +272,51 @@ __device__ __forceinline__ void win_det_add(long long* p, const float v, const f
 // into consecutive accumulators, i.e. one 32-byte sector per four lanes (L2 retires atomics per sector).
 __device__ __forceinline__ int win_det_pos(const int c) { return 8 * (c & 3) + (c >> 2); }
 
-// How the 4 lanes of a group cover the 32 channels of a row: lane sj owns the 16-byte fp32 chunks cA and cA ^ 4
-// (chunk = 4 channels) of every fp32 row (grad_out, grad_value) and the same channels of the value rows;
-// cA = sj for even groups, sj + 4 for odd ones, so that the two groups of a quarter-warp hit different bank
-// halves (conflict-free LDS.128) and the four lanes of one reduction instruction cover 64 contiguous bytes =
-// two whole 32-byte sectors — for bf16 value rows too (their chunk is 8 bytes: two LDS.64 per row).
+// How the lanes of a group cover the 32 channels of a row.  A lane owns kWinNCH 16-byte fp32 chunks (chunk = 4
+// channels) of every fp32 row (grad_out, grad_value) and the same channels of the value rows.
+//   4-lane groups: chunks cA and cA ^ 4, cA = sj for even groups, sj + 4 for odd ones, so that the two groups of a
+//                  quarter-warp hit different bank halves (conflict-free LDS.128) and the four lanes of one reduction
+//                  instruction cover 64 contiguous bytes = two whole 32-byte sectors;
+//   8-lane groups: chunk sj — a quarter-warp reads / reduces one whole 128-byte row.
+// bf16 value rows keep the same channel ownership (their chunk is 8 bytes: LDS.64), so the reductions are full
+// sectors for them too.
 template <typename VT>
 struct WinLane {
   const unsigned char* poolA;  // pool + byte offset of chunk A inside a value row
-  const unsigned char* poolB;
+  const unsigned char* poolB;  // chunk B (4-lane groups only)
   __device__ __forceinline__ WinLane(const unsigned char* pool, const int cA)
       : poolA(pool + cA * 4 * (int)sizeof(VT)), poolB(pool + (cA ^ 4) * 4 * (int)sizeof(VT)) {}
+  static __device__ __forceinline__ void put(const float4 t, float2* v) { v[0] = make_float2(t.x, t.y); v[1] = make_float2(t.z, t.w); }
+  static __device__ __forceinline__ void put(const uint2 t, float2* v) {
+    v[0] = make_float2(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u));
+    v[1] = make_float2(__uint_as_float(t.y << 16), __uint_as_float(t.y & 0xffff0000u));
+  }
   // channels of chunk A -> v[0], v[1]; chunk B -> v[2], v[3]
-  __device__ __forceinline__ void row(const int r, float2 (&v)[4]) const {
+  __device__ __forceinline__ void row(const int r, float2 (&v)[kWinNC2]) const {
     if constexpr (sizeof(VT) == 4) {
-      const float4 lo = *reinterpret_cast<const float4*>(poolA + r * 128);
-      const float4 hi = *reinterpret_cast<const float4*>(poolB + r * 128);
-      v[0] = make_float2(lo.x, lo.y); v[1] = make_float2(lo.z, lo.w);
-      v[2] = make_float2(hi.x, hi.y); v[3] = make_float2(hi.z, hi.w);
+      put(*reinterpret_cast<const float4*>(poolA + r * 128), v);
+      if constexpr (kWinNCH == 2) put(*reinterpret_cast<const float4*>(poolB + r * 128), v + 2);
     } else {
-      const uint2 lo = *reinterpret_cast<const uint2*>(poolA + r * 64);
-      const uint2 hi = *reinterpret_cast<const uint2*>(poolB + r * 64);
-      v[0] = make_float2(__uint_as_float(lo.x << 16), __uint_as_float(lo.x & 0xffff0000u));
-      v[1] = make_float2(__uint_as_float(lo.y << 16), __uint_as_float(lo.y & 0xffff0000u));
-      v[2] = make_float2(__uint_as_float(hi.x << 16), __uint_as_float(hi.x & 0xffff0000u));
-      v[3] = make_float2(__uint_as_float(hi.y << 16), __uint_as_float(hi.y & 0xffff0000u));
+      put(*reinterpret_cast<const uint2*>(poolA + r * 64), v);
+      if constexpr (kWinNCH == 2) put(*reinterpret_cast<const uint2*>(poolB + r * 64), v + 2);
+    }
+  }
+  // the same chunks of a value row in global memory (direct pass); p points at chunk A of the row, dB is the
+  // element distance to chunk B
+  static __device__ __forceinline__ void ldg(const VT* p, const int dB, float2 (&v)[kWinNC2]) {
+    if constexpr (sizeof(VT) == 4) {
+      put(__ldg(reinterpret_cast<const float4*>(p)), v);
+      if constexpr (kWinNCH == 2) put(__ldg(reinterpret_cast<const float4*>(p + dB)), v + 2);
+    } else {
+      put(__ldg(reinterpret_cast<const uint2*>(p)), v);
+      if constexpr (kWinNCH == 2) put(__ldg(reinterpret_cast<const uint2*>(p + dB)), v + 2);
     }
   }
 };
-// The same two chunks of a value row in global memory (direct pass); p points at chunk A of the row, dB is the
-// element distance to chunk B.
-template <typename VT>
-__device__ __forceinline__ void win_ldg_row(const VT* p, const int dB, float2 (&v)[4]) {
-  if constexpr (sizeof(VT) == 4) {
-    const float4 lo = __ldg(reinterpret_cast<const float4*>(p));
-    const float4 hi = __ldg(reinterpret_cast<const float4*>(p + dB));
-    v[0] = make_float2(lo.x, lo.y); v[1] = make_float2(lo.z, lo.w);
-    v[2] = make_float2(hi.x, hi.y); v[3] = make_float2(hi.z, hi.w);
-  } else {
-    const uint2 lo = __ldg(reinterpret_cast<const uint2*>(p));
-    const uint2 hi = __ldg(reinterpret_cast<const uint2*>(p + dB));
-    v[0] = make_float2(__uint_as_float(lo.x << 16), __uint_as_float(lo.x & 0xffff0000u));
-    v[1] = make_float2(__uint_as_float(lo.y << 16), __uint_as_float(lo.y & 0xffff0000u));
-    v[2] = make_float2(__uint_as_float(hi.x << 16), __uint_as_float(hi.x & 0xffff0000u));
-    v[3] = make_float2(__uint_as_float(hi.y << 16), __uint_as_float(hi.y & 0xffff0000u));
-  }
-}
 
-#ifndef MSDA_WIN_BRANCHY_FLUSH
-#define MSDA_WIN_BRANCHY_FLUSH 0
-#endif
-// Adds this lane's 8 channels (chunks cA, cA ^ 4) of a partial row into grad_value row `off` (an element offset
-// inside the image).  Atomic mode: two REDG.E.ADD.F32x4; deterministic mode: eight 64-bit fixed-point adds.
+// Adds this lane's channels of a partial row into grad_value row `off` (an element offset inside the image; off < 0:
+// a pool row outside the image, nothing to add).  Atomic mode: REDG.E.ADD.F32x4 per chunk; deterministic mode:
+// 64-bit fixed-point adds.
 template <bool kDet>
 struct WinRed {
   float* gvA;      // grad_value + image + 4 * cA
@@ -318,32 +324,49 @@ struct WinRed {
   long long* g64;  // deterministic: accumulators + image + cA
   int dB64;        // (cA ^ 4) - cA
   float dscale;
-  // off < 0: nothing to add (a pool row outside the image)
-  __device__ __forceinline__ void operator()(const int off, const float2 (&acc)[4]) const {
+  __device__ __forceinline__ void operator()(const int off, const float2 (&acc)[kWinNC2]) const {
+#if defined(MSDA_WIN_KNOCKOUT) && (MSDA_WIN_KNOCKOUT & 1)
+    if (off == 0x7fffffff) red_add_f4(gvA, acc[0].x, acc[0].y, acc[1].x, acc[1].y);  // never true: keeps the operands alive
+    return;
+#endif
     if constexpr (kDet) {
       if (off >= 0) {
         long long* pa = g64 + off;
-        long long* pb = pa + dB64;
         win_det_add(pa, acc[0].x, dscale); win_det_add(pa + 8, acc[0].y, dscale);
         win_det_add(pa + 16, acc[1].x, dscale); win_det_add(pa + 24, acc[1].y, dscale);
-        win_det_add(pb, acc[2].x, dscale); win_det_add(pb + 8, acc[2].y, dscale);
-        win_det_add(pb + 16, acc[3].x, dscale); win_det_add(pb + 24, acc[3].y, dscale);
+        if constexpr (kWinNCH == 2) {
+          long long* pb = pa + dB64;
+          win_det_add(pb, acc[2].x, dscale); win_det_add(pb + 8, acc[2].y, dscale);
+          win_det_add(pb + 16, acc[3].x, dscale); win_det_add(pb + 24, acc[3].y, dscale);
+        }
       }
-    } else {
-#if MSDA_WIN_BRANCHY_FLUSH
-      if (off >= 0) {
-        red_add_f4(gvA + off, acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-        red_add_f4(gvB + off, acc[2].x, acc[2].y, acc[3].x, acc[3].y);
-      }
-#else
+    } else if constexpr (kWinNCH == 2) {
       red_add_2xf4_if(gvA, gvB, off, acc[0].x, acc[0].y, acc[1].x, acc[1].y, acc[2].x, acc[2].y, acc[3].x, acc[3].y);
-#endif
+    } else {
+      if (off >= 0) red_add_f4(gvA + off, acc[0].x, acc[0].y, acc[1].x, acc[1].y);
     }
   }
 };
 
+// Reduce-scatter of the partial sums of 4 samples over the lanes of a group: afterwards the lane(s) that own sample
+// u hold the group's total of v[u].  4-lane groups: lane u owns sample u; 8-lane groups: lanes 2u and 2u + 1.
+__device__ __forceinline__ float win_reduce_scatter4(float (&v)[4], const int sj, const unsigned gmask) {
+  if constexpr (kWinG == 4) {
+    return group_reduce_scatter<4>(v, sj, gmask);
+  } else {
+    const bool hi = sj & 4;
+    float a0 = hi ? v[2] : v[0], a1 = hi ? v[3] : v[1];
+    a0 += __shfl_xor_sync(gmask, hi ? v[0] : v[2], 4);
+    a1 += __shfl_xor_sync(gmask, hi ? v[1] : v[3], 4);
+    const bool hi2 = sj & 2;
+    float bsum = hi2 ? a1 : a0;
+    bsum += __shfl_xor_sync(gmask, hi2 ? a0 : a1, 2);
+    return bsum + __shfl_xor_sync(gmask, bsum, 1);
+  }
+}
+
 #ifndef MSDA_WIN_BWD_MINBLOCKS
-#define MSDA_WIN_BWD_MINBLOCKS 2
+#define MSDA_WIN_BWD_MINBLOCKS (MSDA_WIN_G == 4 ? 2 : 3)
 #endif
 
 // One block = one tile x one head.  kDet: deterministic grad_value (canonical order inside the block,
@@ -425,7 +448,7 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
                  grad_out + (((size_t)b * Lq + (gq >= 0 ? gq : 0)) * M + m) * 32 + gj * 4, gq >= 0 ? 16 : 0);
     }
   } else {
-    const int gql = t >> 2, gj = t & 3;
+    const int gj = t & 3;
     const int gq = gq_[0];
 #pragma unroll
     for (int c = 0; c < 8; ++c) go_reg[c] = 0.f;
@@ -506,7 +529,11 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
           const bool inb = (unsigned)(wa.hm[l] + rh) < (unsigned)H && (unsigned)(wa.wm[l] + rw) < (unsigned)W;
           const int off = off00 + (rh * W + rw) * M32;
           WIN_CHECK(rw >= 0 && rw < bw && wa.base[l] + r < kWinPool);
+#if defined(MSDA_WIN_KNOCKOUT) && (MSDA_WIN_KNOCKOUT & 2)
+          cp_async16(pool_s + (unsigned)((wa.base[l] + r) * ROWB), src_j, 0);  // zero-fill only: no global read
+#else
           cp_async16(pool_s + (unsigned)((wa.base[l] + r) * ROWB), src_j + (inb ? off : 0), inb ? 16 : 0);
+#endif
           if (jj == 0) rowoff[wa.base[l] + r] = inb ? off : -1;
         }
       }
@@ -629,12 +656,25 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
   // launch, msda_capi.cu); otherwise the wait returns at once
   if (!kDet) asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // lane roles of the sorted and direct passes: 8 groups of 4 lanes per warp, 8 channels per lane
-  const int sg = lane >> 2, sj = lane & 3;
-  const int cA = sj + ((sg & 1) ? 4 : 0), cB = cA ^ 4;
-  const unsigned gmask = 0xfu << (sg * 4);
+  // lane roles of the sorted and direct passes: 32 / kWinG groups of kWinG lanes per warp
+  constexpr int GPW = 32 / kWinG;                 // lane groups per warp
+  const int sg = lane / kWinG, sj = lane % kWinG;
+  const int cA = kWinG == 4 ? sj + ((sg & 1) ? 4 : 0) : sj, cB = cA ^ 4;  // this lane's 16-byte chunk(s) of an fp32 row
+  const unsigned gmask = (kWinG == 4 ? 0xfu : 0xffu) << (sg * kWinG);
   const unsigned char* goA = reinterpret_cast<const unsigned char*>(go_s) + cA * 16;
   const unsigned char* goB = reinterpret_cast<const unsigned char*>(go_s) + cB * 16;
+  // grad_out row of tile query `sq`, this lane's channels as pairs
+  auto load_go = [&](const int sq, float2 (&go)[kWinNC2]) {
+    const float4 a4 = *reinterpret_cast<const float4*>(goA + sq * 128);
+    go[0] = make_float2(a4.x, a4.y); go[1] = make_float2(a4.z, a4.w);
+    if constexpr (kWinNCH == 2) {
+      const float4 b4 = *reinterpret_cast<const float4*>(goB + sq * 128);
+      go[2] = make_float2(b4.x, b4.y); go[3] = make_float2(b4.z, b4.w);
+    }
+  };
+  // which lane parks sample u of a step of 4, and which sample this lane parks
+  const int my_u = kWinG == 4 ? sj : (sj >> 1);
+  const bool parks = kWinG == 4 ? true : (sj & 1) == 0;
   WinRed<kDet> red;
   red.gvA = ar.grad_value + img + cA * 4;
   red.gvB = ar.grad_value + img + cB * 4;
@@ -655,15 +695,19 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
   {
     const WinLane<VT> wl(pool, cA);
     const int total = misc[16], totp = (total + 3) & ~3;   // padded to whole steps of 4 samples
-    constexpr int SNG = kWinThreads / 4;                   // lane groups per block
+    constexpr int SNG = kWinThreads / kWinG;               // lane groups per block
     const int chunk = ((totp / 4 + SNG - 1) / SNG) * 4;
-    const int gi = warp * 8 + sg;
+    const int gi = warp * GPW + sg;
+#if defined(MSDA_WIN_KNOCKOUT) && (MSDA_WIN_KNOCKOUT & 4)
+    const int i0 = 0, i1 = 0;  // knock-out: no sorted pass
+#else
     const int i0 = min(totp, gi * chunk), i1 = min(totp, i0 + chunk);
-    float2 V00[4], V01[4], V10[4], V11[4], A0[4], A1[4], B0[4], B1[4];
+#endif
+    float2 V00[kWinNC2], V01[kWinNC2], V10[kWinNC2], V11[kWinNC2], A0[kWinNC2], A1[kWinNC2], B0[kWinNC2], B1[kWinNC2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) V00[c] = V01[c] = V10[c] = V11[c] = A0[c] = A1[c] = B0[c] = B1[c] = zero2;
+    for (int c = 0; c < kWinNC2; ++c) V00[c] = V01[c] = V10[c] = V11[c] = A0[c] = A1[c] = B0[c] = B1[c] = zero2;
     int cur0 = kWinPool, cur1 = kWinPool;  // the all-zero rows: nothing to flush
-    auto flush = [&](const int row, const float2 (&acc)[4]) {
+    auto flush = [&](const int row, const float2 (&acc)[kWinNC2]) {
       WIN_CHECK(row >= 0 && row < kWinPool + 2);
       const int off = rowoff[row];
       WIN_CHECK(off < 0 || (off % 32 == 0 && off / 32 < S * M));
@@ -680,8 +724,8 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
         const int sq = sid_of(pk, u) / LP;
         const float4 r = rnext;
         // grad_out row of the sample's query; the next sample's record is fetched one step ahead
-        const float4 ga4 = *reinterpret_cast<const float4*>(goA + sq * 128);
-        const float4 gb4 = *reinterpret_cast<const float4*>(goB + sq * 128);
+        float2 go[kWinNC2];
+        load_go(sq, go);
         rnext = rec[rec_slot(u < 3 ? sid_of(pk, u + 1) : sid_of(pk_next, 0))];
         const int code = __float_as_int(r.x);
         const int row0 = code & 0xffff, row1 = code >> 16;
@@ -695,7 +739,7 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
             flush(cur1 + 1, B1);
           }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < kWinNC2; ++c) {
             A0[c] = adj ? A1[c] : zero2;
             B0[c] = adj ? B1[c] : zero2;
             A1[c] = zero2;
@@ -710,8 +754,6 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
         const float lh = r.y, lw = r.z, a = r.w;
         aws[u] = a;
         const float hh = 1.f - lh, hw = 1.f - lw;
-        const float2 go[4] = {make_float2(ga4.x, ga4.y), make_float2(ga4.z, ga4.w), make_float2(gb4.x, gb4.y),
-                              make_float2(gb4.z, gb4.w)};
         // grad_value partial sums (cuh:125,134,143,152): independent of the value rows, so they cover
         // the latency of a window reload
         const float c00 = hh * hw, c01 = hh * lw, c10 = lh * hw, c11 = lh * lw;
@@ -719,13 +761,13 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
         const float2 w00p = make_float2(w00, w00), w01p = make_float2(w01, w01), w10p = make_float2(w10, w10),
                      w11p = make_float2(w11, w11);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < kWinNC2; ++c) {
           A0[c] = ffma2(w00p, go[c], A0[c]); A1[c] = ffma2(w01p, go[c], A1[c]);
           B0[c] = ffma2(w10p, go[c], B0[c]); B1[c] = ffma2(w11p, go[c], B1[c]);
         }
         float2 e00 = zero2, e01 = zero2, e10 = zero2, e11 = zero2;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < kWinNC2; ++c) {
           e00 = ffma2(go[c], V00[c], e00); e01 = ffma2(go[c], V01[c], e01);
           e10 = ffma2(go[c], V10[c], e10); e11 = ffma2(go[c], V11[c], e11);
         }
@@ -736,14 +778,14 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
         pgx[u] = a * fmaf(hh, d01 - d00, lh * (d11 - d10));
         pgy[u] = a * fmaf(hw, d10 - d00, lw * (d11 - d01));
       }
-      const float gx = group_reduce_scatter<4>(pgx, sj, gmask);
-      const float gy = group_reduce_scatter<4>(pgy, sj, gmask);
-      const float ga = group_reduce_scatter<4>(pga, sj, gmask);
-      // lane sj owns sample ib + sj: park its gradients in the sample's record slot (.w keeps the sample's
+      const float gx = win_reduce_scatter4(pgx, sj, gmask);
+      const float gy = win_reduce_scatter4(pgy, sj, gmask);
+      const float ga = win_reduce_scatter4(pga, sj, gmask);
+      // the lane that owns sample ib + my_u parks its gradients in the sample's record slot (.w keeps the sample's
       // weight: the fused prologue's softmax backward needs it); padding entries have no slot of their own
-      const int sid = sj == 0 ? sid_of(pk, 0) : sj == 1 ? sid_of(pk, 1) : sj == 2 ? sid_of(pk, 2) : sid_of(pk, 3);
-      if (sid < Cfg::PAD_SID)
-        rec[rec_slot(sid)] = make_float4(gx, gy, ga, sj == 0 ? aws[0] : sj == 1 ? aws[1] : sj == 2 ? aws[2] : aws[3]);
+      const int sid = my_u == 0 ? sid_of(pk, 0) : my_u == 1 ? sid_of(pk, 1) : my_u == 2 ? sid_of(pk, 2) : sid_of(pk, 3);
+      if (parks && sid < Cfg::PAD_SID)
+        rec[rec_slot(sid)] = make_float4(gx, gy, ga, my_u == 0 ? aws[0] : my_u == 1 ? aws[1] : my_u == 2 ? aws[2] : aws[3]);
     }
     flush(cur0, A0);
     flush(cur1, B0);
@@ -755,66 +797,71 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
   __syncwarp();
   if (lane == 0) { const long long n = clock64(); atomicAdd(&g_win_timing[warp], (unsigned long long)(n - t_dbg)); t_dbg = n; }
 #endif
-  // ---- phase 5: direct pass — levels that did not get a window; one 4-lane group per query --------------
+  // ---- phase 5: direct pass — levels that did not get a window; one lane group per query ------------------
   {
     int lbase[kL];
     bool all_win = true;
 #pragma unroll
     for (int l = 0; l < kL; ++l) { lbase[l] = misc[20 + l]; all_win = all_win && lbase[l] >= 0; }
+#if defined(MSDA_WIN_KNOCKOUT) && (MSDA_WIN_KNOCKOUT & 8)
+    all_win = true;  // knock-out: no direct pass
+#endif
     if (!all_win) {
-      const int dql = warp * 8 + sg;
-      const float4 ga4 = *reinterpret_cast<const float4*>(goA + dql * 128);
-      const float4 gb4 = *reinterpret_cast<const float4*>(goB + dql * 128);
-      const float2 go[4] = {make_float2(ga4.x, ga4.y), make_float2(ga4.z, ga4.w), make_float2(gb4.x, gb4.y),
-                            make_float2(gb4.z, gb4.w)};
       const VT* value_A = value_img + cA * 4;
       const int dB = (cB - cA) * 4;
+#pragma unroll 1
+      for (int dql = warp * GPW + sg; dql < kWinTileQ; dql += (kWinThreads / 32) * GPW) {
+        float2 go[kWinNC2];
+        load_go(dql, go);
 #pragma unroll
-      for (int l = 0; l < kL; ++l) {
-        if (lbase[l] >= 0) continue;  // block-uniform
-        const int o_line = lv.W[l] * M32;
-        float4 r[4];
+        for (int l = 0; l < kL; ++l) {
+          if (lbase[l] >= 0) continue;  // block-uniform
+          const int o_line = lv.W[l] * M32;
+          float4 r[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) r[i] = rec[dql * RS + l * 4 + i];
-        float pgx[4], pgy[4], pga[4];
+          for (int i = 0; i < 4; ++i) r[i] = rec[dql * RS + l * 4 + i];
+          float pgx[4], pgy[4], pga[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int code = __float_as_int(r[i].x);
-          // the four row loads of a point go out together; the reductions below carry no memory clobber, so
-          // the compiler is free to hoist the next point's loads above them
-          float2 v[4][4];
+          for (int i = 0; i < 4; ++i) {
+            const int code = __float_as_int(r[i].x);
+            // the four row loads of a point go out together; the reductions below carry no memory clobber, so
+            // the compiler is free to hoist the next point's loads above them
+            float2 v[4][kWinNC2];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 4; ++k) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) v[k][c] = zero2;
-            if (code & (1 << k)) win_ldg_row<VT>(value_A + (code & ~31) + ((k & 2) ? o_line : 0) + ((k & 1) ? M32 : 0), dB, v[k]);
-          }
-          const float lh = r[i].y, lw = r[i].z, a = r[i].w;
-          const float hh = 1.f - lh, hw = 1.f - lw;
-          const float a_hh = a * hh, a_lh = a * lh;
-          float d[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float2 e = zero2;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) e = ffma2(go[c], v[k][c], e);
-            d[k] = e.x + e.y;
-            if (code & (1 << k)) {
-              const float tt = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
-              float2 acc[4];
-#pragma unroll
-              for (int c = 0; c < 4; ++c) acc[c] = make_float2(tt * go[c].x, tt * go[c].y);
-              red((code & ~31) + ((k & 2) ? o_line : 0) + ((k & 1) ? M32 : 0), acc);
+              for (int c = 0; c < kWinNC2; ++c) v[k][c] = zero2;
+              if (code & (1 << k))
+                WinLane<VT>::ldg(value_A + (code & ~31) + ((k & 2) ? o_line : 0) + ((k & 1) ? M32 : 0), dB, v[k]);
             }
+            const float lh = r[i].y, lw = r[i].z, a = r[i].w;
+            const float hh = 1.f - lh, hw = 1.f - lw;
+            const float a_hh = a * hh, a_lh = a * lh;
+            float d[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float2 e = zero2;
+#pragma unroll
+              for (int c = 0; c < kWinNC2; ++c) e = ffma2(go[c], v[k][c], e);
+              d[k] = e.x + e.y;
+              if (code & (1 << k)) {
+                const float tt = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
+                float2 acc[kWinNC2];
+#pragma unroll
+                for (int c = 0; c < kWinNC2; ++c) acc[c] = make_float2(tt * go[c].x, tt * go[c].y);
+                red((code & ~31) + ((k & 2) ? o_line : 0) + ((k & 1) ? M32 : 0), acc);
+              }
+            }
+            pga[i] = hh * (hw * d[0] + lw * d[1]) + lh * (hw * d[2] + lw * d[3]);
+            pgx[i] = a * (hh * (d[1] - d[0]) + lh * (d[3] - d[2]));
+            pgy[i] = a * (hw * (d[2] - d[0]) + lw * (d[3] - d[1]));
           }
-          pga[i] = hh * (hw * d[0] + lw * d[1]) + lh * (hw * d[2] + lw * d[3]);
-          pgx[i] = a * (hh * (d[1] - d[0]) + lh * (d[3] - d[2]));
-          pgy[i] = a * (hw * (d[2] - d[0]) + lw * (d[3] - d[1]));
+          const float gx = win_reduce_scatter4(pgx, sj, gmask);
+          const float gy = win_reduce_scatter4(pgy, sj, gmask);
+          const float ga = win_reduce_scatter4(pga, sj, gmask);
+          if (parks)
+            rec[dql * RS + l * 4 + my_u] = make_float4(gx, gy, ga, my_u == 0 ? r[0].w : my_u == 1 ? r[1].w : my_u == 2 ? r[2].w : r[3].w);
         }
-        const float gx = group_reduce_scatter<4>(pgx, sj, gmask);
-        const float gy = group_reduce_scatter<4>(pgy, sj, gmask);
-        const float ga = group_reduce_scatter<4>(pga, sj, gmask);
-        rec[dql * RS + l * 4 + sj] = make_float4(gx, gy, ga, sj == 0 ? r[0].w : sj == 1 ? r[1].w : sj == 2 ? r[2].w : r[3].w);
       }
     }
   }
