@@ -324,9 +324,19 @@ struct WinRed {
   long long* g64;  // deterministic: accumulators + image + cA
   int dB64;        // (cA ^ 4) - cA
   float dscale;
+  int spread_rows; // knock-out experiments only
   __device__ __forceinline__ void operator()(const int off, const float2 (&acc)[kWinNC2]) const {
 #if defined(MSDA_WIN_KNOCKOUT) && (MSDA_WIN_KNOCKOUT & 1)
     if (off == 0x7fffffff) red_add_f4(gvA, acc[0].x, acc[0].y, acc[1].x, acc[1].y);  // never true: keeps the operands alive
+    return;
+#endif
+#if defined(MSDA_WIN_KNOCKOUT) && (MSDA_WIN_KNOCKOUT & 16)
+    // same number of reductions, but every block scatters them over the whole image instead of its own (shared, hot) rows
+    if (off >= 0) {
+      const int rows = spread_rows;
+      const int r2 = (int)(((unsigned)(off >> 5) * 2654435761u + blockIdx.x * 40503u) % (unsigned)rows);
+      red_add_2xf4_if(gvA, gvB, r2 << 5, acc[0].x, acc[0].y, acc[1].x, acc[1].y, acc[kWinNC2 - 2].x, acc[kWinNC2 - 2].y, acc[kWinNC2 - 1].x, acc[kWinNC2 - 1].y);
+    }
     return;
 #endif
     if constexpr (kDet) {
@@ -681,6 +691,7 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
   red.g64 = kDet ? ar.gv64 + img + cA : nullptr;
   red.dB64 = cB - cA;
   red.dscale = kDet ? win_det_scale(ar.maxbits, Lq, LP) : 0.f;
+  red.spread_rows = S * M;
   const float2 zero2 = make_float2(0.f, 0.f);
   auto sid_of = [](const uint2 pk, const int u) {
     return (int)(u == 0 ? pk.x & 0xffffu : u == 1 ? pk.x >> 16 : u == 2 ? pk.y & 0xffffu : pk.y >> 16);
@@ -771,6 +782,11 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
           e00 = ffma2(go[c], V00[c], e00); e01 = ffma2(go[c], V01[c], e01);
           e10 = ffma2(go[c], V10[c], e10); e11 = ffma2(go[c], V11[c], e11);
         }
+#if defined(MSDA_WIN_EXTRA_FMA)
+        // issue-sensitivity experiment: MSDA_WIN_EXTRA_FMA independent FFMA2 per sample that feed nothing that matters
+#pragma unroll
+        for (int x = 0; x < MSDA_WIN_EXTRA_FMA; ++x) e00 = ffma2(make_float2(1e-30f, 1e-30f), go[x % kWinNC2], e00);
+#endif
         const float d00 = e00.x + e00.y, d01 = e01.x + e01.y, d10 = e10.x + e10.y, d11 = e11.x + e11.y;
         // this lane's channels of grad_attn_weight (cuh:156) and of grad_sampling_loc (cuh:157-158) before the
         // factors W_l, H_l, which the write-out applies
