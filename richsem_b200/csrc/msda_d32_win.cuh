@@ -534,6 +534,9 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
         // approximation error is below 1e-4 for r < 2^15, so the truncation is exact
         const float inv_bw = __fdividef(1.f, (float)bw);
         const int off00 = ((lv.start[l] + wa.hm[l] * W + wa.wm[l]) * M + m) * 32;
+#if defined(MSDA_WIN_KNOCKOUT) && (MSDA_WIN_KNOCKOUT & 32)
+        if (t >= 0) continue;  // knock-out: no staging loop at all (use together with bit 0: row offsets stay unset)
+#endif
         for (int r = r0; r < n; r += kWinThreads / G) {
           const int rh = (int)(((float)r + 0.5f) * inv_bw), rw = r - rh * bw;
           const bool inb = (unsigned)(wa.hm[l] + rh) < (unsigned)H && (unsigned)(wa.wm[l] + rw) < (unsigned)W;
