@@ -12,8 +12,10 @@ Error behaviour mirrors the reference: precondition failures raise RuntimeError 
 AT_ASSERTM); CPU tensors raise "Not implemented on the CPU" (ms_deform_attn.h:38).  Kernel launch
 failures also raise (the reference only printf()s them).
 
-Beyond the reference: bfloat16 ``value`` (fp32 locations / weights, bf16 output, fp32 gradients),
-and a deterministic grad_value mode (see ``set_deterministic``).
+Beyond the reference: bfloat16 ``value`` (fp32 locations / weights, bf16 output; ``ms_deform_attn_backward`` returns
+fp32 gradients — the autograd Function then casts grad_value to the bf16 input's dtype, as autograd requires), a
+deterministic grad_value mode (``set_deterministic``) and the choice of pixel-coordinate arithmetic
+(``set_coords_fma``).
 """
 from __future__ import annotations
 
@@ -26,13 +28,26 @@ from . import _capi
 _SUFFIX = {torch.float32: "f32", torch.float64: "f64", torch.bfloat16: "bf16"}
 _FWD = {k: getattr(_capi.lib, "msda_forward_" + k) for k in ("f32", "f64", "bf16")}
 _BWD = {k: getattr(_capi.lib, "msda_backward_" + k) for k in ("f32", "f64", "bf16")}
-_state = {"deterministic": os.environ.get("MSDA_B200_DETERMINISTIC", "0") not in ("", "0")}
+_state = {"deterministic": os.environ.get("MSDA_B200_DETERMINISTIC", "0") not in ("", "0"),
+          "coords_fma": os.environ.get("MSDA_B200_COORDS_FMA", "0") not in ("", "0")}
 _workspaces: dict = {}
 
 
 def set_deterministic(flag: bool) -> None:
     """grad_value by sort-by-corner segmented sums (bitwise reproducible) instead of fp32 atomics."""
     _state["deterministic"] = bool(flag)
+
+
+def set_coords_fma(flag: bool) -> None:
+    """Pixel coordinate = fma(loc, size, -0.5) instead of the default round(loc * size) - 0.5.
+
+    The default is the reference SOURCE (ms_deform_im2col_cuda.cuh:285-286, a rounded multiply followed by a rounded
+    subtract) and is what every parity claim of this repo refers to.  nvcc compiles that source line with -fmad=true
+    into ONE fused multiply-add, so the reference's shipped binary computes the fused form; the two differ only where
+    loc * size rounds onto the pixel lattice — every sample of an un-jittered initialisation (zero offset weights,
+    integer-pixel offset bias), where the floor cell flips and grad_sampling_loc takes the other one-sided derivative.
+    Set this (or MSDA_B200_COORDS_FMA=1) to reproduce the compiled reference sample for sample."""
+    _state["coords_fma"] = bool(flag)
 
 
 def is_deterministic() -> bool:
@@ -201,6 +216,8 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     out = torch.empty(p.out_shape, dtype=value.dtype, device=value.device)
     if out.numel() == 0:
         return out
+    if _state["coords_fma"]:
+        _flags |= _capi.FLAG_COORDS_FMA
     n, s, m, d, nl, lq, npt = p.dims
     with _on_device(value.device):
         rc = _FWD[p.sfx](
@@ -246,6 +263,8 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
         return [grad_value.zero_() if _need_grad_value else None, grad_loc, grad_attw]
     n, s, m, d, nl, lq, npt = p.dims
     flags, ws = _flags, None
+    if _state["coords_fma"]:
+        flags |= _capi.FLAG_COORDS_FMA
     if not _need_grad_value:
         flags |= _capi.FLAG_NO_GRAD_VALUE
     if (_state["deterministic"] or torch.are_deterministic_algorithms_enabled()) and value.dtype != torch.float64:

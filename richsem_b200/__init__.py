@@ -10,7 +10,7 @@ there is no CPU or PyTorch fallback.
 """
 from . import _capi  # noqa: F401  (loads the CUDA library or raises)
 from . import MultiScaleDeformableAttention  # noqa: F401
-from .MultiScaleDeformableAttention import is_deterministic, set_deterministic  # noqa: F401
+from .MultiScaleDeformableAttention import is_deterministic, set_coords_fma, set_deterministic  # noqa: F401
 
 __version__ = "0.1.0"
 

@@ -40,10 +40,11 @@ class MSDeformAttn(nn.Module):
     Extra (not in the reference):
         value_dtype: ``None`` keeps the reference behaviour (value in the input dtype);
             ``torch.bfloat16`` stores the projected value and the sampled output in bf16
-            (fp32 accumulation, fp32 gradients).
+            (fp32 accumulation; the kernels return fp32 gradients, and autograd hands value_proj a grad_value rounded to
+            this dtype).
         fuse_prologue: compute the softmax and the sampling locations inside the kernels
-            (``MSDeformAttnFusedFunction``) wherever the library supports it — large encoder-style
-            calls — instead of five elementwise PyTorch kernels around the op.  Same results within
+            (``MSDeformAttnFusedFunction``) wherever the library supports it — encoder self-attention and
+            decoder-sized cross-attention calls — instead of five elementwise PyTorch kernels around the op.  Same results within
             the op's tolerances; ``None`` reads ``MSDA_B200_FUSE_PROLOGUE`` (default off).
     """
 
