@@ -60,6 +60,10 @@ constexpr int kWinNCH = 8 / kWinG;    // 16-byte fp32 chunks of a row held by on
 #define MSDA_WIN_POOL (MSDA_WIN_G == 4 ? 448 : 320)
 #endif
 constexpr int kWinPool = MSDA_WIN_POOL;
+// Order in which the grid walks the tiles (1: last to first, see the kernel).
+#ifndef MSDA_WIN_REVERSE
+#define MSDA_WIN_REVERSE 1
+#endif
 
 // Index checks for debug builds (MSDA_NVCC_EXTRA=-DMSDA_WIN_CHECKS): compute-sanitizer is not available on
 // the GPU pool, so the shared-memory indices of this kernel are asserted by hand; a failed check traps.
@@ -401,7 +405,12 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
 
   const int M = kM ? kM : ar.M, Lq = ar.Lq, S = ar.S, M32 = M * 32;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int m = blockIdx.x % M, tile = blockIdx.x / M, b = blockIdx.y;
+  // Tiles are handed out last to first: the host's patch order ends with the coarse levels' queries, whose tiles are
+  // the expensive ones (their fine-level samples do not fit the pool and take the direct pass) — started first, they
+  // do not end up alone in the kernel's tail.
+  const int m = blockIdx.x % M, b = blockIdx.y;
+  const int tile = MSDA_WIN_REVERSE ? (int)(gridDim.x / M) - 1 - (int)(blockIdx.x / M) : (int)(blockIdx.x / M);
+  constexpr int kPfStep = MSDA_WIN_REVERSE ? -kWinPrefetchTiles : kWinPrefetchTiles;  // the tile one wave of blocks later
   const int* order = ar.order;
   const int order_len = ar.order_len;
   const VT* grad_out = static_cast<const VT*>(ar.grad_out);
@@ -413,12 +422,12 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
   const int ql = t & (kWinTileQ - 1), slot = t / kWinTileQ;
   auto tile_query = [&](const int tl, const int k) {
     const int os = tl * kWinTileQ + k;
-    return os < order_len ? (order ? order[os] : os) : -1;
+    return (os >= 0 && os < order_len) ? (order ? order[os] : os) : -1;
   };
   // every order entry this thread needs is requested before the first load that depends on one (one L2 round trip
   // instead of three back to back)
   const int q = tile_query(tile, ql);
-  const int qpf = tile_query(tile + kWinPrefetchTiles, ql);
+  const int qpf = tile_query(tile + kPfStep, ql);
   int gq_[2];
   if constexpr (sizeof(VT) == 4) {
     gq_[0] = tile_query(tile, t >> 3);
@@ -840,40 +849,48 @@ msda_bwd_d32_win_kernel(const WinBwdArgs ar, const __grid_constant__ MsdaLevels 
 #pragma unroll
           for (int i = 0; i < 4; ++i) r[i] = rec[dql * RS + l * 4 + i];
           float pgx[4], pgy[4], pga[4];
+          // two points at a time: their eight row loads go out together (the registers of the sorted pass's rows and
+          // accumulators are free here), so a level costs two L2 round trips per query instead of four
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int code = __float_as_int(r[i].x);
-            // the four row loads of a point go out together; the reductions below carry no memory clobber, so
-            // the compiler is free to hoist the next point's loads above them
-            float2 v[4][kWinNC2];
+          for (int ip = 0; ip < 4; ip += 2) {
+            float2 v[2][4][kWinNC2];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int ii = 0; ii < 2; ++ii) {
+              const int code = __float_as_int(r[ip + ii].x);
 #pragma unroll
-              for (int c = 0; c < kWinNC2; ++c) v[k][c] = zero2;
-              if (code & (1 << k))
-                WinLane<VT>::ldg(value_A + (code & ~31) + ((k & 2) ? o_line : 0) + ((k & 1) ? M32 : 0), dB, v[k]);
-            }
-            const float lh = r[i].y, lw = r[i].z, a = r[i].w;
-            const float hh = 1.f - lh, hw = 1.f - lw;
-            const float a_hh = a * hh, a_lh = a * lh;
-            float d[4];
+              for (int k = 0; k < 4; ++k) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float2 e = zero2;
-#pragma unroll
-              for (int c = 0; c < kWinNC2; ++c) e = ffma2(go[c], v[k][c], e);
-              d[k] = e.x + e.y;
-              if (code & (1 << k)) {
-                const float tt = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
-                float2 acc[kWinNC2];
-#pragma unroll
-                for (int c = 0; c < kWinNC2; ++c) acc[c] = make_float2(tt * go[c].x, tt * go[c].y);
-                red((code & ~31) + ((k & 2) ? o_line : 0) + ((k & 1) ? M32 : 0), acc);
+                for (int c = 0; c < kWinNC2; ++c) v[ii][k][c] = zero2;
+                if (code & (1 << k))
+                  WinLane<VT>::ldg(value_A + (code & ~31) + ((k & 2) ? o_line : 0) + ((k & 1) ? M32 : 0), dB, v[ii][k]);
               }
             }
-            pga[i] = hh * (hw * d[0] + lw * d[1]) + lh * (hw * d[2] + lw * d[3]);
-            pgx[i] = a * (hh * (d[1] - d[0]) + lh * (d[3] - d[2]));
-            pgy[i] = a * (hw * (d[2] - d[0]) + lw * (d[3] - d[1]));
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) {
+              const int i = ip + ii;
+              const int code = __float_as_int(r[i].x);
+              const float lh = r[i].y, lw = r[i].z, a = r[i].w;
+              const float hh = 1.f - lh, hw = 1.f - lw;
+              const float a_hh = a * hh, a_lh = a * lh;
+              float d[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float2 e = zero2;
+#pragma unroll
+                for (int c = 0; c < kWinNC2; ++c) e = ffma2(go[c], v[ii][k][c], e);
+                d[k] = e.x + e.y;
+                if (code & (1 << k)) {
+                  const float tt = ((k & 2) ? a_lh : a_hh) * ((k & 1) ? lw : hw);
+                  float2 acc[kWinNC2];
+#pragma unroll
+                  for (int c = 0; c < kWinNC2; ++c) acc[c] = make_float2(tt * go[c].x, tt * go[c].y);
+                  red((code & ~31) + ((k & 2) ? o_line : 0) + ((k & 1) ? M32 : 0), acc);
+                }
+              }
+              pga[i] = hh * (hw * d[0] + lw * d[1]) + lh * (hw * d[2] + lw * d[3]);
+              pgx[i] = a * (hh * (d[1] - d[0]) + lh * (d[3] - d[2]));
+              pgy[i] = a * (hw * (d[2] - d[0]) + lw * (d[3] - d[1]));
+            }
           }
           const float gx = win_reduce_scatter4(pgx, sj, gmask);
           const float gy = win_reduce_scatter4(pgy, sj, gmask);
