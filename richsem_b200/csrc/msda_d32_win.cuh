@@ -42,7 +42,10 @@ namespace msda {
 // Queries per block (one 8x8 patch of the host's order); 4 threads per query (one per level slot).  Half patches
 // (32 queries, 128 threads, four blocks per SM with a 256-row pool) measured 0.413 ms against 0.344 ms per bs=2 encoder
 // layer: 40 % more window cells and staged rows per query outweigh the finer-grained overlap of the blocks' phases.
-constexpr int kWinTileQ = 64;
+#ifndef MSDA_WIN_TILEQ
+#define MSDA_WIN_TILEQ 64
+#endif
+constexpr int kWinTileQ = MSDA_WIN_TILEQ;
 constexpr int kWinThreads = 4 * kWinTileQ;
 // Lanes per lane group of the sorted and direct passes (the group covers the 32 channels of a row):
 //   4 lanes x 8 channels: value rows + accumulators = 64 registers per thread -> 128 registers, two blocks per SM,
