@@ -223,6 +223,26 @@ int msda_rowmax_f32(msda_stream_t stream, const float* logits, long long rows, i
 int msda_topk_rows_f32(msda_stream_t stream, const float* scores, int batch, int row_len, int k, int64_t* indices,
                        float* values);
 
+/* ---- encoder-layer epilogue: residual add + LayerNorm ----
+ * models/richsem/deformable_transformer.py:871-872 (`src = src + self.dropout1(src2); src = self.norm1(src)`) and
+ * :866-867 (the same around the FFN), dropout 0 as RichSem trains (config/RichSem/baseline_4scale.py:42):
+ *   out[row,:] = (y - mean(y)) * rstd(y) * gamma + beta,   y = x[row,:] + residual[row,:]
+ * x / residual / out / grad_* are [rows, channels] fp32, channels a multiple of 128 up to 512 (else
+ * MSDA_ERR_UNSUPPORTED); residual may be NULL (plain LayerNorm), gamma / beta may be NULL (1 / 0); biased variance,
+ * rstd = 1 / sqrt(var + eps) as torch.nn.LayerNorm.  mean / rstd [rows] are the statistics the backward wants (both
+ * NULL: not stored).
+ * The backward writes grad_in = d loss / d y — the gradient of x AND of residual — and, when grad_gamma / grad_beta are
+ * given, their sums over the rows in a fixed order (bitwise reproducible), through a caller-provided DEVICE workspace
+ * of msda_add_layernorm_workspace_bytes(rows, channels). */
+int msda_add_layernorm_f32(msda_stream_t stream, const float* x, const float* residual, const float* gamma,
+                           const float* beta, long long rows, int channels, float eps, float* out, float* mean,
+                           float* rstd);
+int msda_add_layernorm_backward_f32(msda_stream_t stream, const float* grad_out, const float* x, const float* residual,
+                                    const float* gamma, const float* mean, const float* rstd, long long rows,
+                                    int channels, float* grad_in, float* grad_gamma, float* grad_beta, void* workspace,
+                                    size_t workspace_bytes);
+size_t msda_add_layernorm_workspace_bytes(long long rows, int channels);
+
 /* ---- index contract probe --------------------------------------------------
  * Writes, for every sample (b,q,m,l,p), the four bilinear corner token indices
  * (level_start_index[l] + h*W_l + w, i.e. an index into the spatial_size axis)

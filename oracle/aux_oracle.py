@@ -4,6 +4,8 @@ TEST INFRASTRUCTURE ONLY — imported by tests/ (and nothing in richsem_b200/). 
 
 * ``value_prepare``      /root/reference/models/richsem/ops/modules/ms_deform_attn.py:94-97
 * ``encoder_proposals``  /root/reference/models/richsem/utils.py:10-65 (gen_encoder_output_proposals)
+* ``add_layer_norm``     /root/reference/models/richsem/deformable_transformer.py:871-872, 866-867
+                         (``src = src + dropout(src2); src = norm(src)``, dropout 0)
 
 Pinned: ``encoder_proposals`` is bit-identical to the reference function loaded by path in the build
 container (tests/test_oracle.py::test_aux_oracle_matches_the_reference_function) and to the golden vectors in
@@ -84,3 +86,18 @@ def load_reference_proposals(reference_root="/root/reference"):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.gen_encoder_output_proposals
+
+
+def add_layer_norm(x, residual, weight, bias, eps=1e-5, dtype=torch.float64):
+    """deformable_transformer.py:871-872: ``norm(src + src2)`` with nn.LayerNorm's definition (biased variance,
+    ``(y - mean) / sqrt(var + eps) * weight + bias``), written out in ``dtype`` (fp64 by default: the kernels are
+    compared against the exact result, torch's own fp32 kernel is a second witness in the tests)."""
+    y = x.to(dtype) if residual is None else x.to(dtype) + residual.to(dtype)
+    mean = y.mean(-1, keepdim=True)
+    var = ((y - mean) ** 2).mean(-1, keepdim=True)
+    out = (y - mean) / torch.sqrt(var + eps)
+    if weight is not None:
+        out = out * weight.to(dtype)
+    if bias is not None:
+        out = out + bias.to(dtype)
+    return out

@@ -86,6 +86,14 @@ def _load():
     lib.msda_rowmax_f32.restype = _i
     lib.msda_topk_rows_f32.argtypes = [_vp, _vp, _i, _i, _i, _vp, _vp]
     lib.msda_topk_rows_f32.restype = _i
+    _f = ctypes.c_float
+    lib.msda_add_layernorm_f32.argtypes = [_vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp, _vp, _vp]
+    lib.msda_add_layernorm_f32.restype = _i
+    lib.msda_add_layernorm_backward_f32.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp,
+                                                    ctypes.c_size_t]
+    lib.msda_add_layernorm_backward_f32.restype = _i
+    lib.msda_add_layernorm_workspace_bytes.argtypes = [_ll, _i]
+    lib.msda_add_layernorm_workspace_bytes.restype = ctypes.c_size_t
     lib.msda_debug_corners_f32.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, opts_p]
     lib.msda_debug_corners_f32.restype = _i
     lib.msda_backward_workspace_bytes.argtypes = [_i] * 7

@@ -187,35 +187,53 @@ msda_add_layernorm_bwd_kernel(const float* __restrict__ go, const float* __restr
   }
 }
 
-// grad_gamma[c] = sum over blocks of partial[block][0][c], grad_beta[c] likewise from [1]; one thread per (which, c),
-// the blocks in index order.
-__global__ void __launch_bounds__(256)
+// grad_gamma[c] = sum over blocks of partial[block][0][c], grad_beta[c] likewise from [1].  Block = 32 columns x 32 slices
+// of the block range: every thread has its ~14 loads in flight at once, then the slices are added in index order (fixed
+// order: bitwise reproducible).
+__global__ void __launch_bounds__(1024)
 msda_layernorm_param_grad_kernel(const float* __restrict__ partial, const int nblocks, const int C,
                                  float* __restrict__ grad_gamma, float* __restrict__ grad_beta) {
-  const int k = blockIdx.x * 256 + threadIdx.x;
-  if (k >= 2 * C) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int b = 0;
-  for (; b + 4 <= nblocks; b += 4) {
-    s0 += partial[(size_t)b * 2 * C + k];
-    s1 += partial[(size_t)(b + 1) * 2 * C + k];
-    s2 += partial[(size_t)(b + 2) * 2 * C + k];
-    s3 += partial[(size_t)(b + 3) * 2 * C + k];
+  __shared__ float part[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + tx;  // (which, channel) as one index < 2 * C; 2 * C is a multiple of 32
+  float s = 0.f;
+#pragma unroll 4
+  for (int b = ty; b < nblocks; b += 32) s += partial[(size_t)b * 2 * C + k];
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tot += part[j][tx];
+    if (k < C) {
+      if (grad_gamma) grad_gamma[k] = tot;
+    } else if (grad_beta) {
+      grad_beta[k - C] = tot;
+    }
   }
-  for (; b < nblocks; ++b) s0 += partial[(size_t)b * 2 * C + k];
-  const float s = (s0 + s1) + (s2 + s3);
-  if (k < C) {
-    if (grad_gamma) grad_gamma[k] = s;
-  } else if (grad_beta) {
-    grad_beta[k - C] = s;
+}
+
+// Blocks of the backward kernel: what is resident at once (registers bound it: 3 blocks per SM at 256 channels), so that
+// there are as few partial sums as possible.
+template <int NV>
+int ln_bwd_grid(const long long rows) {
+  static int per_sm = 0;  // benign race: every thread computes the same value
+  if (per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, msda_add_layernorm_bwd_kernel<NV>, kLnThreads, 0) != cudaSuccess || n < 1) n = 2;
+    per_sm = n > kLnBlocksPerSm ? kLnBlocksPerSm : n;
   }
+  long long blocks = (rows + kLnWarps - 1) / kLnWarps;
+  const long long cap = (long long)kSms * per_sm;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int check_dims(const long long rows, const int channels) {
-  if (rows < 0 || channels < 128 || channels > 1024 || (channels & 127))
-    return fail(MSDA_ERR_UNSUPPORTED, "rows=%lld channels=%d: channels must be a multiple of 128 up to 1024", rows, channels);
+  if (rows < 0 || channels < 128 || channels > 512 || (channels & 127))
+    return fail(MSDA_ERR_UNSUPPORTED, "rows=%lld channels=%d: channels must be a multiple of 128 up to 512", rows, channels);
   return MSDA_OK;
 }
 }  // namespace
@@ -243,7 +261,7 @@ int msda_add_layernorm_f32(msda_stream_t stream, const float* x, const float* re
     msda_add_layernorm_kernel<NV><<<grid, kLnThreads, 0, s>>>(x, residual, gamma, beta, out, mean, rstd, rows, eps); \
     break;
   switch (channels / 128) {
-    MSDA_LN_FWD(1) MSDA_LN_FWD(2) MSDA_LN_FWD(3) MSDA_LN_FWD(4) MSDA_LN_FWD(5) MSDA_LN_FWD(6) MSDA_LN_FWD(7) MSDA_LN_FWD(8)
+    MSDA_LN_FWD(1) MSDA_LN_FWD(2) MSDA_LN_FWD(3) MSDA_LN_FWD(4)
   }
 #undef MSDA_LN_FWD
   return after_launch("msda_add_layernorm_kernel");
@@ -268,20 +286,21 @@ int msda_add_layernorm_backward_f32(msda_stream_t stream, const float* grad_out,
   if (want_params && (!workspace || workspace_bytes < msda_add_layernorm_workspace_bytes(rows, channels)))
     return fail(MSDA_ERR_WORKSPACE, "grad_gamma / grad_beta need %zu bytes of workspace, got %zu",
                 msda_add_layernorm_workspace_bytes(rows, channels), workspace_bytes);
-  const int grid = ln_grid(rows);
+  int grid = 1;
   float* partial = want_params ? static_cast<float*>(workspace) : nullptr;
 #define MSDA_LN_BWD(NV)                                                                                     \
   case NV:                                                                                                  \
+    grid = ln_bwd_grid<NV>(rows);                                                                           \
     msda_add_layernorm_bwd_kernel<NV><<<grid, kLnThreads, 0, s>>>(grad_out, x, residual, gamma, mean, rstd, \
                                                                   grad_in, partial, rows);                  \
     break;
   switch (channels / 128) {
-    MSDA_LN_BWD(1) MSDA_LN_BWD(2) MSDA_LN_BWD(3) MSDA_LN_BWD(4) MSDA_LN_BWD(5) MSDA_LN_BWD(6) MSDA_LN_BWD(7) MSDA_LN_BWD(8)
+    MSDA_LN_BWD(1) MSDA_LN_BWD(2) MSDA_LN_BWD(3) MSDA_LN_BWD(4)
   }
 #undef MSDA_LN_BWD
   if (int rc = after_launch("msda_add_layernorm_bwd_kernel")) return rc;
   if (want_params) {
-    msda_layernorm_param_grad_kernel<<<(2 * channels + 255) / 256, 256, 0, s>>>(partial, grid, channels, grad_gamma, grad_beta);
+    msda_layernorm_param_grad_kernel<<<2 * channels / 32, 1024, 0, s>>>(partial, grid, channels, grad_gamma, grad_beta);
     return after_launch("msda_layernorm_param_grad_kernel");
   }
   return MSDA_OK;

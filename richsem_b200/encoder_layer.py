@@ -6,8 +6,9 @@ Mirrors the structure and parameter names of the reference
 (/root/reference/models/richsem/deformable_transformer.py:825-881 ``DeformableTransformerEncoderLayer``: self_attn,
 norm1, linear1, linear2, norm2; :470-618 ``TransformerEncoder``: ``layers``) so a reference state dict loads; dropout
 and the optional channel attention are left out — the RichSem config trains with dropout 0.0
-(config/RichSem/baseline_4scale.py:42).  Everything but the sampling core and its elementwise neighbours is stock
-PyTorch (cuBLAS GEMMs, LayerNorm).
+(config/RichSem/baseline_4scale.py:42).  The sampling core, its elementwise neighbours and the two residual +
+LayerNorm epilogues (:871-872, :866-867; one pass each, csrc/msda_layernorm.cu) are this library's kernels; the Linear
+layers are stock PyTorch (cuBLAS GEMMs).
 """
 from __future__ import annotations
 
@@ -15,13 +16,15 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .ops.functions.aux_functions import add_layer_norm
 from .ops.modules import MSDeformAttn
 
 
 class DeformableEncoderLayer(nn.Module):
     def __init__(self, d_model=256, d_ffn=2048, n_levels=4, n_heads=8, n_points=4, value_dtype=None,
-                 fuse_prologue=None):
+                 fuse_prologue=None, fuse_epilogue=True):
         super().__init__()
+        self.fuse_epilogue = fuse_epilogue  # residual add + LayerNorm in one kernel (False: the PyTorch expressions)
         self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points, value_dtype=value_dtype,
                                       fuse_prologue=fuse_prologue)
         self.norm1 = nn.LayerNorm(d_model)
@@ -31,8 +34,11 @@ class DeformableEncoderLayer(nn.Module):
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask=None):
         query = src if pos is None else src + pos
-        src = self.norm1(src + self.self_attn(query, reference_points, src, spatial_shapes, level_start_index,
-                                              key_padding_mask))
+        src2 = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, key_padding_mask)
+        if self.fuse_epilogue and src.is_cuda:
+            src = add_layer_norm(src, src2, self.norm1)
+            return add_layer_norm(src, self.linear2(F.relu(self.linear1(src))), self.norm2)
+        src = self.norm1(src + src2)
         return self.norm2(src + self.linear2(F.relu(self.linear1(src))))
 
 

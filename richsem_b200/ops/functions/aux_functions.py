@@ -7,6 +7,9 @@ C ABI: include/msda_b200.h, kernels: csrc/msda_aux.cu).
 * ``gen_encoder_output_proposals`` — same name, arguments and results as the reference helper
   (/root/reference/models/richsem/utils.py:10-65), one kernel pass instead of ~25 PyTorch kernels.
 
+* ``add_layer_norm`` — ``norm(src + src2)``, the encoder layer's epilogue around ``output_proj`` and around the FFN
+  (/root/reference/models/richsem/deformable_transformer.py:871-872, 866-867), one pass forward and one backward.
+
 CUDA only, like everything in this package: CPU tensors raise.
 """
 from __future__ import annotations
@@ -219,3 +222,74 @@ def topk_proposals(enc_outputs_class: torch.Tensor, topk: int) -> torch.Tensor:
     — the indices of the ``topk`` tokens with the largest best-class logit, (N, topk) int64.  Not differentiable
     (indices), like the reference expression."""
     return topk_rows(class_scores(enc_outputs_class), topk)
+
+
+class AddLayerNormFunction(Function):
+    """``F.layer_norm(x + residual, (C,), weight, bias, eps)`` in one kernel pass, with its gradients."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, eps):
+        if not x.is_cuda:
+            raise RuntimeError("Not implemented on the CPU")
+        _require(x.dtype == torch.float32, "x must be fp32")
+        _require(residual is None or (residual.shape == x.shape and residual.dtype == x.dtype and residual.is_cuda),
+                 "residual must match x")
+        c = x.shape[-1]
+        _require(weight is None or (weight.numel() == c and weight.dtype == torch.float32), "weight must be (C,) fp32")
+        _require(bias is None or (bias.numel() == c and bias.dtype == torch.float32), "bias must be (C,) fp32")
+        x = x.contiguous()
+        residual = None if residual is None else residual.contiguous()
+        weight = None if weight is None else weight.contiguous()
+        bias = None if bias is None else bias.contiguous()
+        rows = x.numel() // c if x.numel() else 0
+        out = torch.empty_like(x)
+        stats = torch.empty(2, rows, dtype=torch.float32, device=x.device)  # mean, rstd
+        with _on_device(x.device):
+            _capi.check(_capi.lib.msda_add_layernorm_f32(
+                _stream(x.device), x.data_ptr(), None if residual is None else residual.data_ptr(),
+                None if weight is None else weight.data_ptr(), None if bias is None else bias.data_ptr(), rows, c,
+                float(eps), out.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr()), "msda_add_layernorm_f32")
+        ctx.save_for_backward(x, residual, weight, stats)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        x, residual, weight, stats = ctx.saved_tensors
+        c = x.shape[-1]
+        rows = stats.shape[1]
+        grad_out = grad_out.contiguous()
+        grad_in = torch.empty_like(x)
+        want_w = weight is not None and ctx.needs_input_grad[2]
+        want_b = ctx.has_bias and ctx.needs_input_grad[3]
+        gw = torch.empty(c, dtype=torch.float32, device=x.device) if want_w else None
+        gb = torch.empty(c, dtype=torch.float32, device=x.device) if want_b else None
+        ws_bytes = _capi.lib.msda_add_layernorm_workspace_bytes(rows, c) if (want_w or want_b) else 0
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+        with _on_device(x.device):
+            _capi.check(_capi.lib.msda_add_layernorm_backward_f32(
+                _stream(x.device), grad_out.data_ptr(), x.data_ptr(), None if residual is None else residual.data_ptr(),
+                None if weight is None else weight.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), rows, c,
+                grad_in.data_ptr(), None if gw is None else gw.data_ptr(), None if gb is None else gb.data_ptr(),
+                None if ws is None else ws.data_ptr(), ws_bytes), "msda_add_layernorm_backward_f32")
+        return (grad_in if ctx.needs_input_grad[0] else None,
+                grad_in if residual is not None and ctx.needs_input_grad[1] else None, gw, gb, None)
+
+
+def add_layer_norm_supported(x, residual=None) -> bool:
+    """What the kernels serve: fp32 CUDA rows of 128 * k channels, k <= 4 (RichSem: d_model 256)."""
+    c = x.shape[-1] if x.dim() else 0
+    return (x.is_cuda and x.dtype == torch.float32 and c % 128 == 0 and 128 <= c <= 512
+            and (residual is None or (residual.is_cuda and residual.dtype == torch.float32 and residual.shape == x.shape)))
+
+
+def add_layer_norm(x, residual, norm: "torch.nn.LayerNorm | None" = None, weight=None, bias=None, eps=1e-5):
+    """``norm(x + residual)`` (deformable_transformer.py:871-872): pass the ``nn.LayerNorm`` module, or weight / bias /
+    eps.  Shapes the kernels do not serve take the two-kernel PyTorch expression."""
+    if norm is not None:
+        weight, bias, eps = norm.weight, norm.bias, norm.eps
+    if not add_layer_norm_supported(x, residual):
+        y = x if residual is None else x + residual
+        return torch.nn.functional.layer_norm(y, (y.shape[-1],), weight, bias, eps)
+    return AddLayerNormFunction.apply(x, residual, weight, bias, eps)

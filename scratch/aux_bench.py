@@ -64,6 +64,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--iters", type=int, default=60)
     ap.add_argument("--sets", type=int, default=8)
+    ap.add_argument("--only", default="", help="'layernorm': just the residual + LayerNorm passes")
     a = ap.parse_args()
     dev = "cuda:0"
     shapes = syn.level_shapes(800, 1333)
@@ -82,6 +83,55 @@ def main():
                           "GBps": gbs, "frac_of_hbm_peak": gbs / pk, "peak_GBps": pk, "torch_ms": torch_ms,
                           "speedup_vs_torch": torch_ms / ms, "note": note}))
 
+    # 8f-3 epilogue: norm(src + src2), forward (read 2 tensors, write 1) and backward (read 3, write 1)
+    from richsem_b200.ops.functions.aux_functions import AddLayerNormFunction
+
+    norm = torch.nn.LayerNorm(c).to(dev)
+    rs = [torch.randn(n, S, c, device=dev) for _ in range(a.sets)]
+    full = rows * c * 4
+    ms = timeit([lambda x=x, r=r: AddLayerNormFunction.apply(x, r, norm.weight.detach(), norm.bias.detach(), 1e-5)
+                 for x, r in zip(xs, rs)], a.iters)
+    tms = timeit([lambda x=x, r=r: torch.nn.functional.layer_norm(x + r, (c,), norm.weight.detach(), norm.bias.detach())
+                  for x, r in zip(xs, rs)], a.iters)
+    report("add_layernorm_fwd", ms, 3 * full + rows * 8, tms, "vs F.layer_norm(x + r) (two kernels, five tensor passes)")
+
+    def fwd_bwd(fn, x, r):
+        x = x.detach().requires_grad_(True)
+        r = r.detach().requires_grad_(True)
+        norm.zero_grad(set_to_none=True)
+        fn(x, r).backward(rs[0])
+        return x.grad
+
+    ms2 = timeit([lambda x=x, r=r: fwd_bwd(lambda u, v: AddLayerNormFunction.apply(u, v, norm.weight, norm.bias, 1e-5), x, r)
+                  for x, r in zip(xs, rs)], a.iters)
+    tms2 = timeit([lambda x=x, r=r: fwd_bwd(lambda u, v: norm(u + v), x, r) for x, r in zip(xs, rs)], a.iters)
+    report("add_layernorm_fwd_bwd", ms2, 7 * full + 3 * rows * 8, tms2,
+           "forward + backward incl. weight / bias gradients, vs norm(x + r) under autograd")
+    # the backward pass alone, through the C ABI (no autograd bookkeeping around it)
+    from richsem_b200 import _capi
+    from richsem_b200.MultiScaleDeformableAttention import _stream
+
+    stats = torch.empty(2, rows, device=dev)
+    _capi.check(_capi.lib.msda_add_layernorm_f32(_stream(xs[0].device), xs[0].data_ptr(), rs[0].data_ptr(), norm.weight.data_ptr(),
+                                                 norm.bias.data_ptr(), rows, c, 1e-5, torch.empty_like(xs[0]).data_ptr(),
+                                                 stats[0].data_ptr(), stats[1].data_ptr()), "fwd")
+    ws_bytes = _capi.lib.msda_add_layernorm_workspace_bytes(rows, c)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    gin = [torch.empty_like(x) for x in xs]
+    gw, gb = torch.empty(c, device=dev), torch.empty(c, device=dev)
+
+    def bwd_only(k):
+        # statistics of set 0 for every set: timing only
+        _capi.check(_capi.lib.msda_add_layernorm_backward_f32(
+            _stream(xs[0].device), rs[(k + 1) % len(rs)].data_ptr(), xs[k].data_ptr(), rs[k].data_ptr(), norm.weight.data_ptr(),
+            stats[0].data_ptr(), stats[1].data_ptr(), rows, c, gin[k].data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(),
+            ws_bytes), "bwd")
+
+    ms3 = timeit([lambda k=k: bwd_only(k) for k in range(len(xs))], a.iters)
+    report("add_layernorm_bwd_c_abi", ms3, 4 * full + 2 * rows * 8, float("nan"), "backward kernels alone (grad_in + weight / bias gradients)")
+    del rs, gin
+    if a.only == "layernorm":
+        return
     # 8f-2, bf16: read fp32 (unmasked rows) + mask, write bf16
     alg = (rows - masked_rows) * c * 4 + rows + rows * c * 2
     ms = timeit([lambda x=x: cast_value_bf16(x, mask) for x in xs], a.iters)

@@ -367,3 +367,69 @@ def test_randomized_proposals_and_selection_sweep():
         assert torch.equal(sc.gather(1, got), want_val), (it, shapes, kc, k)
         for b in range(n):
             assert len(set(got[b].tolist())) == k
+
+
+# ---- encoder-layer epilogue: residual add + LayerNorm (8f-3) ------------------------------------------------------
+@pytest.mark.parametrize("rows_shape,c", [((2, 22223), 256), ((3, 41), 128), ((1, 1), 512), ((5, 7), 384)])
+@pytest.mark.parametrize("with_residual", [True, False])
+def test_add_layer_norm_forward_and_backward_against_the_oracle(rows_shape, c, with_residual):
+    """out and all gradients against the fp64 expression of oracle/aux_oracle.py (autograd on the CPU); torch's own fp32
+    LayerNorm kernel on the same inputs sets the scale of an acceptable fp32 error."""
+    from richsem_b200.ops.functions.aux_functions import AddLayerNormFunction
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(*rows_shape, c, generator=g) * 2 + 0.3
+    r = torch.randn(*rows_shape, c, generator=g) if with_residual else None
+    w = torch.randn(c, generator=g) * 0.5 + 1
+    b = torch.randn(c, generator=g) * 0.1
+    go = torch.randn(*rows_shape, c, generator=g)
+
+    leaves = [t.double().requires_grad_(True) if t is not None else None for t in (x, r, w, b)]
+    want = ao.add_layer_norm(*leaves, eps=1e-5)
+    want.backward(go.double())
+
+    dl = [t.cuda().requires_grad_(True) if t is not None else None for t in (x, r, w, b)]
+    got = AddLayerNormFunction.apply(*dl, 1e-5)
+    got.backward(go.cuda())
+    assert rel_err(got.detach().cpu(), want.detach()) < 2e-6
+    for name, a, e in zip(("x", "residual", "weight", "bias"), dl, leaves):
+        if a is None:
+            continue
+        # parameter gradients are sums over up to 44,446 rows: fp32 accumulation error grows with sqrt(rows)
+        tol = 2e-5 if name in ("weight", "bias") else 5e-6
+        assert rel_err(a.grad.cpu(), e.grad) < tol, name
+    # second witness: torch's fp32 kernel
+    y = x.cuda() if r is None else x.cuda() + r.cuda()
+    torch_out = torch.nn.functional.layer_norm(y, (c,), w.cuda(), b.cuda(), 1e-5)
+    assert rel_err(got.detach(), torch_out) < 2e-6
+
+
+def test_add_layer_norm_parameter_gradients_are_bitwise_reproducible_and_edges():
+    from richsem_b200.ops.functions import add_layer_norm
+    from richsem_b200.ops.functions.aux_functions import AddLayerNormFunction, add_layer_norm_supported
+
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 22223, 256, generator=g).cuda()
+    r = torch.randn(2, 22223, 256, generator=g).cuda()
+    go = torch.randn(2, 22223, 256, generator=g).cuda()
+    norm = torch.nn.LayerNorm(256).cuda()
+    runs = []
+    for _ in range(3):
+        norm.zero_grad()
+        xx = x.clone().requires_grad_(True)
+        add_layer_norm(xx, r, norm).backward(go)
+        runs.append((norm.weight.grad.clone(), norm.bias.grad.clone(), xx.grad.clone()))
+    for k in range(3):
+        assert torch.equal(runs[0][k], runs[1][k]) and torch.equal(runs[0][k], runs[2][k])
+    # no parameters / no gradient wanted for them; empty input; unsupported widths take the PyTorch expression
+    out = AddLayerNormFunction.apply(x[:, :9], r[:, :9], None, None, 1e-5)
+    assert rel_err(out, torch.nn.functional.layer_norm(x[:, :9] + r[:, :9], (256,))) < 2e-6
+    assert AddLayerNormFunction.apply(x[:, :0], r[:, :0], norm.weight, norm.bias, 1e-5).shape == (2, 0, 256)
+    z = torch.randn(4, 6, 96, device="cuda")
+    assert not add_layer_norm_supported(z)
+    n96 = torch.nn.LayerNorm(96).cuda()
+    assert torch.equal(add_layer_norm(z, z, n96), n96(z + z))
+    with pytest.raises(RuntimeError):
+        AddLayerNormFunction.apply(z, z, None, None, 1e-5)
+    with pytest.raises(RuntimeError):
+        AddLayerNormFunction.apply(x.cpu(), None, None, None, 1e-5)
