@@ -91,6 +91,8 @@ def parse_args():
     ap.add_argument("--eager", action="store_true", help="encoder_stack6: no CUDA graph")
     ap.add_argument("--fuse-prologue", action="store_true", help="encoder_stack6: fused softmax + "
                     "sampling-location prologue (SURVEY 8f-1)")
+    ap.add_argument("--no-fuse-epilogue", action="store_true", help="encoder_stack6: residual + LayerNorm as the two "
+                    "PyTorch kernels instead of the library's one-pass kernel")
     ap.add_argument("--tf32", action="store_true", help="encoder_stack6: let the PyTorch Linear layers use TF32 tensor "
                     "cores (torch.backends.cuda.matmul.allow_tf32); the default is the reference's strict fp32")
     ap.add_argument("--padding", action="store_true", help="encoder_stack6: image 1 of each pair is padded (mask path)")
@@ -668,7 +670,7 @@ def run_encoder_stack(args, c):
     shapes = syn.level_shapes(*hw)
     shp, st, S = syn.level_tensors(shapes, dev)
     torch.manual_seed(1234)
-    model = DeformableEncoder(layers, fuse_prologue=args.fuse_prologue).to(dev)
+    model = DeformableEncoder(layers, fuse_prologue=args.fuse_prologue, fuse_epilogue=not args.no_fuse_epilogue).to(dev)
     with torch.no_grad():  # leave the degenerate init so that every gradient path does real work
         for layer in model.layers:
             layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
@@ -733,11 +735,11 @@ def run_encoder_stack(args, c):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "image": f"{hw[0]}x{hw[1]}", "S": S, "batch_per_gpu": bs,
                        "layers_per_step": layers, "params": n_params, "mode": "eager" if args.eager else "cuda graph",
-                       "fuse_prologue": bool(args.fuse_prologue), "padding_mask": bool(args.padding),
+                       "fuse_prologue": bool(args.fuse_prologue), "fuse_epilogue": not args.no_fuse_epilogue, "padding_mask": bool(args.padding),
                        "linear_precision": "tf32" if args.tf32 else "fp32 (reference default)",
                        "parallelism": f"replicas x{world}, no collective",
                        "step": "6-layer deformable encoder fwd + bwd (MSDeformAttn + elementwise neighbours on "
-                               "libmsda_b200, Linears/LayerNorm/FFN in PyTorch), no optimizer"},
+                               "libmsda_b200, residual + LayerNorm on libmsda_b200 unless fuse_epilogue is false, Linears / FFN in PyTorch), no optimizer"},
             # a replayed graph launches the library's kernels without passing through its host entry points:
             # the count below is what the capture recorded times the replays
             "gpu_launches": int(launches) if args.eager else int(launches_per_step * args.steps),

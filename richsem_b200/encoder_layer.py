@@ -73,10 +73,10 @@ class DeformableEncoder(nn.Module):
     computed once and shared by all layers."""
 
     def __init__(self, num_layers=6, d_model=256, d_ffn=2048, n_levels=4, n_heads=8, n_points=4, value_dtype=None,
-                 fuse_prologue=None):
+                 fuse_prologue=None, fuse_epilogue=True):
         super().__init__()
         self.layers = nn.ModuleList(DeformableEncoderLayer(d_model, d_ffn, n_levels, n_heads, n_points, value_dtype,
-                                                           fuse_prologue) for _ in range(num_layers))
+                                                           fuse_prologue, fuse_epilogue) for _ in range(num_layers))
 
     def forward(self, src, pos, spatial_shapes, level_start_index, valid_ratios, key_padding_mask=None,
                 reference_points=None):
