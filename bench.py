@@ -633,8 +633,8 @@ def run_encoder_layer_ddp(c, steps, warmup):
     return {"value": c.world * bs * S / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "dtype": "f32",
             "config": {"workload": "encoder_layer_ddp", "image": f"{hw[0]}x{hw[1]}", "S": S, "batch_per_gpu": bs,
                        "params": n_params,
-                       "step": "encoder layer fwd + bwd (MSDeformAttn on libmsda_b200, Linears / LayerNorm / FFN in "
-                               "PyTorch fp32), no optimizer"},
+                       "step": "encoder layer fwd + bwd (MSDeformAttn and residual + LayerNorm on libmsda_b200, "
+                               "Linears / FFN in PyTorch fp32), no optimizer"},
             "arm": {"parallelism": f"DDP x{c.world}: bucketed NCCL all-reduce of {n_params * 4 / 1e6:.2f} MB of fp32 "
                                    "gradients per step" if c.world > 1 else "1 GPU: the same step, no wrapper, no collective"},
             "ms_per_step_without_ddp_wrapper": local_ms, "allreduce_exposed_ms": ms - local_ms,
