@@ -160,3 +160,32 @@ def test_encoder_reference_points_match_the_linspace_formulation():
     got = get_reference_points(shapes, vr)
     assert got.shape == (2, sum(h * w for h, w in shapes), 4, 2)
     assert torch.equal(got, want)
+
+
+def test_add_layer_norm_host_side_selection_and_oracle_expression():
+    """Residual + LayerNorm (deformable_transformer.py:871-872): what the kernels do not serve (CPU tensors, widths that
+    are not a multiple of 128) takes the PyTorch expression; the kernel entry point itself refuses CPU tensors; the
+    oracle's fp64 expression agrees with nn.LayerNorm."""
+    from oracle import aux_oracle as ao
+    from richsem_b200.ops.functions import add_layer_norm
+    from richsem_b200.ops.functions.aux_functions import AddLayerNormFunction, add_layer_norm_supported
+
+    g = torch.Generator().manual_seed(9)
+    x, r = torch.randn(2, 5, 256, generator=g), torch.randn(2, 5, 256, generator=g)
+    norm = torch.nn.LayerNorm(256)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+        norm.bias.uniform_(-0.1, 0.1)
+    assert not add_layer_norm_supported(x, r)  # CPU
+    assert torch.equal(add_layer_norm(x, r, norm), norm(x + r))
+    assert torch.equal(add_layer_norm(x, None, weight=norm.weight, bias=norm.bias, eps=norm.eps), norm(x))
+    with pytest.raises(RuntimeError, match="CPU"):
+        AddLayerNormFunction.apply(x, r, norm.weight, norm.bias, 1e-5)
+    want = ao.add_layer_norm(x, r, norm.weight, norm.bias, norm.eps)
+    assert (want - norm(x + r).double()).abs().max() < 1e-5
+    # the C ABI's argument checks need no GPU
+    lib = richsem_b200._capi.lib
+    assert lib.msda_add_layernorm_workspace_bytes(44446, 256) >= 2 * 256 * 4
+    assert lib.msda_add_layernorm_f32(None, None, None, None, None, 10, 96, 1e-5, None, None, None) == 2  # UNSUPPORTED
+    assert b"multiple of 128" in lib.msda_last_error()
+    assert lib.msda_add_layernorm_f32(None, None, None, None, None, 0, 256, 1e-5, None, None, None) == 0  # empty: nothing to do
