@@ -504,6 +504,113 @@ def run_legacy_cuda(c, sets, ours_fwd_ms, ours_bwd_ms):
             "speedup_fwd_bwd": (f_ms + b_ms) / (ours_fwd_ms + ours_bwd_ms), "input_sets": len(sets)}
 
 
+def run_aux_passes(c, iters=48, n_sets=4):
+    """The HBM-bound passes either side of the sampling core at the headline shape (bs = 2,
+    S = 22,223, C = 256), each against its own roofline: algorithmic bytes / time / measured HBM peak.  Inputs rotate over
+    n_sets distinct buffers (4 x 45.5 MB > the 126 MB L2); one round over all sets is captured in a CUDA graph and the
+    graph is replayed, so the figures are device time (the passes take 10-40 us, less than a Python launch)."""
+    torch, _capi, syn = c.torch, c._capi, c.syn
+    from richsem_b200.MultiScaleDeformableAttention import _stream
+    from richsem_b200.ops.functions import gen_encoder_output_proposals, topk_proposals
+    from richsem_b200.ops.functions.aux_functions import cast_value_bf16, class_scores
+
+    dev = c.dev
+    shapes = syn.level_shapes(800, 1333)
+    shp, _, S = syn.level_tensors(shapes, dev)
+    n, ch = 2, 256
+    rows = n * S
+    full = rows * ch * 4
+    pk = peaks()[0]
+    gen = torch.Generator(device=dev).manual_seed(99)
+    xs = [torch.randn(n, S, ch, generator=gen, device=dev) for _ in range(n_sets)]
+    rs = [torch.randn(n, S, ch, generator=gen, device=dev) for _ in range(n_sets)]
+    parts = []
+    for i in range(n):  # image 1: right 30 % / bottom 20 % of every level is padding
+        fh, fw = (1.0, 1.0) if i % 2 == 0 else (0.8, 0.7)
+        lv = []
+        for h, w in shapes:
+            m = torch.ones(h, w, dtype=torch.bool)
+            m[: max(1, round(h * fh)), : max(1, round(w * fw))] = False
+            lv.append(m.reshape(-1))
+        parts.append(torch.cat(lv))
+    mask = torch.stack(parts).to(dev)
+    masked = int(mask.sum())
+
+    def timeit(fns):
+        for f in fns:
+            f()
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                keep = [f() for f in fns]
+        torch.cuda.current_stream(dev).wait_stream(side)
+        rounds = max(1, iters // len(fns))
+        g.replay()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(rounds):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        del keep, g
+        return e0.elapsed_time(e1) / (rounds * len(fns))
+
+    out = {}
+
+    def put(name, ms, alg, ref):
+        gbs = alg / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "algorithmic_bytes": alg, "GBps": gbs, "frac": gbs / pk, "reference": ref}
+
+    l0 = _capi.launch_count()
+    # residual add + LayerNorm (deformable_transformer.py:871-872), forward and backward through the C ABI
+    gamma, beta = torch.rand(ch, device=dev) + 0.5, torch.randn(ch, device=dev) * 0.1
+    outs = [torch.empty_like(x) for x in xs]
+    stats = torch.empty(2, rows, device=dev)
+
+    def ln_fwd(k):
+        _capi.check(_capi.lib.msda_add_layernorm_f32(_stream(dev), xs[k].data_ptr(), rs[k].data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                                     rows, ch, 1e-5, outs[k].data_ptr(), stats[0].data_ptr(), stats[1].data_ptr()),
+                    "msda_add_layernorm_f32")
+
+    put("add_layernorm_fwd", timeit([lambda k=k: ln_fwd(k) for k in range(n_sets)]), 3 * full + rows * 8,
+        "src = norm(src + src2), deformable_transformer.py:871-872")
+    ws_bytes = _capi.lib.msda_add_layernorm_workspace_bytes(rows, ch)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    gw, gb = torch.empty(ch, device=dev), torch.empty(ch, device=dev)
+
+    def ln_bwd(k):  # grad_out = another set's residual; the statistics of the last forward serve every set (timing only)
+        _capi.check(_capi.lib.msda_add_layernorm_backward_f32(
+            _stream(dev), rs[(k + 1) % n_sets].data_ptr(), xs[k].data_ptr(), rs[k].data_ptr(), gamma.data_ptr(), stats[0].data_ptr(),
+            stats[1].data_ptr(), rows, ch, outs[k].data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), ws_bytes),
+            "msda_add_layernorm_backward_f32")
+
+    put("add_layernorm_bwd", timeit([lambda k=k: ln_bwd(k) for k in range(n_sets)]), 4 * full + 2 * rows * 8,
+        "its backward incl. weight / bias gradients (two kernels)")
+    del outs, rs
+    # value preparation (ms_deform_attn.py:94-97): mask zeroing + bf16 cast
+    put("value_prepare_bf16", timeit([lambda x=x: cast_value_bf16(x, mask) for x in xs]),
+        (rows - masked) * ch * 4 + rows + rows * ch * 2, "value.masked_fill(mask, 0).to(bf16), ms_deform_attn.py:94-97")
+    # two-stage proposals (utils.py:10-65)
+    keep_rows = int(torch.isfinite(gen_encoder_output_proposals(xs[0], mask, shp)[1][..., 0]).sum())
+    put("encoder_proposals", timeit([lambda x=x: gen_encoder_output_proposals(x, mask, shp) for x in xs]),
+        keep_rows * ch * 4 + rows + rows * ch * 4 + rows * 16, "gen_encoder_output_proposals, utils.py:10-65")
+    del xs
+    # query selection (deformable_transformer.py:367-369), 91 classes
+    ls = [torch.randn(n, S, 91, generator=gen, device=dev) for _ in range(n_sets)]
+    put("class_scores_K91", timeit([lambda x=x: class_scores(x) for x in ls]), rows * 91 * 4 + rows * 4,
+        "enc_outputs_class.max(-1)[0], deformable_transformer.py:369")
+    put("topk_proposals_K91_k900", timeit([lambda x=x: topk_proposals(x, 900) for x in ls]),
+        rows * 91 * 4 + 2 * rows * 4 + n * 900 * 8, "torch.topk(scores, 900, dim=1)[1], :367-369 (latency-bound: one cluster per image)")
+    out["_note"] = ("bs=2, S=22223, C=256; CUDA-graph replay over %d rotating buffer sets (larger than L2); frac = algorithmic "
+                    "bytes / time / measured HBM peak" % n_sets)
+    out["_launches_per_round"] = int(_capi.launch_count() - l0)
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------
@@ -538,7 +645,7 @@ def run_b200(args):
         res = time_op_workload(c, args.workload, args.steps, args.warmup, graph=args.graph, deterministic=args.deterministic,
                                lib_flags=args.lib_flags, kernel=args.kernel, want_e2e=not args.no_e2e,
                                e2e_steps=args.e2e_steps, keep_sets=sets)
-        extras, legacy = None, None
+        extras, legacy, aux = None, None, None
         if default_line:
             if rank == 0:
                 legacy = run_legacy_cuda(c, sets[:4], res["roofline_fwd_bwd"]["fwd_ms_per_layer"],
@@ -551,6 +658,9 @@ def run_b200(args):
                 extras[key] = compact(time_op_workload(c, name, min(args.steps, 50), args.warmup, min_seconds=0.25, **opt))
             torch.cuda.empty_cache()
             extras["encoder_layer_ddp"] = run_encoder_layer_ddp(c, min(args.steps, 50), args.warmup)
+            torch.cuda.empty_cache()
+            aux = run_aux_passes(c) if rank == 0 else None
+            sync_all(c)
         if rank == 0:
             cpu_baseline = None
             if world == 1 and not args.no_cpu_baseline:
@@ -566,6 +676,7 @@ def run_b200(args):
             if extras is not None:
                 line["workloads"] = extras
                 line["legacy_cuda"] = legacy
+                line["aux_passes"] = aux
             print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
