@@ -17,7 +17,9 @@ line, "workloads": every other BASELINE config (decoder6 eager and graph-replaye
 shapes, atomic and deterministic, and the DDP encoder-layer step — on every N, 1 included), each with its own
 value / ms_per_step / roofline / clocks, and "legacy_cuda": the reference's own CUDA kernels (recompiled for
 sm_100a, oracle/_ref) timed on the same B200 and the same inputs — a comparator leg outside the product's timed
-region.  --no-extra skips both.
+region — and "aux_passes": the HBM-bound passes either side of the op (residual + LayerNorm, value preparation,
+proposals, query selection) at the headline shape, each against its own roofline (rank 0 only).
+--no-extra skips all three.
 
 One process per GPU (torchrun for N>1); the op never communicates (images are independent), so ranks
 only meet at the barriers around the timed region; value = queries processed by all ranks / max-over-ranks
