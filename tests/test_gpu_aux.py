@@ -433,3 +433,28 @@ def test_add_layer_norm_parameter_gradients_are_bitwise_reproducible_and_edges()
         AddLayerNormFunction.apply(z, z, None, None, 1e-5)
     with pytest.raises(RuntimeError):
         AddLayerNormFunction.apply(x.cpu(), None, None, None, 1e-5)
+
+
+def test_encoder_layer_with_fused_epilogue_under_inference_mode_and_switch():
+    """The layer's one-pass residual + LayerNorm runs under torch.inference_mode() (eval setup) and gives what the
+    two-kernel PyTorch expression gives (fuse_epilogue=False) on the same parameters."""
+    from richsem_b200 import synthetic as syn
+    from richsem_b200.encoder_layer import DeformableEncoderLayer, encoder_reference_points
+
+    shapes = [(20, 27), (10, 14), (5, 7), (3, 4)]
+    dev = "cuda:0"
+    shp, starts, S = syn.level_tensors(shapes, dev)
+    torch.manual_seed(21)
+    layer = DeformableEncoderLayer().to(dev).eval()
+    with torch.no_grad():
+        layer.self_attn.sampling_offsets.weight.normal_(0, 0.02)
+        layer.norm1.weight.uniform_(0.5, 1.5)
+        layer.norm2.bias.uniform_(-0.2, 0.2)
+    src, pos = torch.randn(2, S, 256, device=dev), torch.randn(2, S, 256, device=dev)
+    ref = encoder_reference_points(shapes, 2, dev)
+    with torch.inference_mode():
+        fused = layer(src, pos, ref, shp, starts, None)
+    layer.fuse_epilogue = False
+    with torch.no_grad():
+        plain = layer(src, pos, ref, shp, starts, None)
+    assert rel_err(fused, plain) < 5e-6
