@@ -335,3 +335,71 @@ def test_graphed_step_refreshes_masks_and_rejects_other_level_tables():
     assert la != lb and abs(lb - want) <= 1e-5 * abs(want)
     with pytest.raises(ValueError):
         step(src, pos, shp + 1, starts, valid, m1)
+
+
+@pytest.mark.parametrize("fuse_prologue", [False, True])
+def test_decoder_layer_against_the_reference_layer_expressions(fuse_prologue):
+    """The caller of BASELINE config 3: DeformableDecoderLayer against the reference layer's expression sequence
+    (deformable_transformer.py:965-974 self-attention, :998-1003 cross-attention with 4-d reference boxes through
+    ms_deform_attn.py:98-111, :941-945 FFN; dropout 0) evaluated on the CPU with the grid_sample oracle as the sampling
+    core."""
+    import copy
+
+    import torch.nn.functional as F
+
+    from oracle.msda_oracle import core_pytorch
+    from richsem_b200 import synthetic as syn
+    from richsem_b200.decoder_layer import DeformableDecoderLayer
+
+    shapes = [(20, 27), (10, 14), (5, 7), (3, 4)]
+    dev = "cuda:0"
+    shp, starts, S = syn.level_tensors(shapes, dev)
+    nq, bs = 37, 2
+    torch.manual_seed(17)
+    layer = DeformableDecoderLayer(fuse_prologue=fuse_prologue).to(dev)
+    with torch.no_grad():
+        layer.cross_attn.sampling_offsets.weight.normal_(0, 0.02)
+        layer.cross_attn.attention_weights.weight.normal_(0, 0.1)
+    tgt = torch.randn(nq, bs, 256, device=dev)
+    qpos = torch.randn(nq, bs, 256, device=dev)
+    memory = torch.randn(S, bs, 256, device=dev)
+    boxes = torch.cat([torch.rand(nq, bs, 1, 2, device=dev), torch.rand(nq, bs, 1, 2, device=dev) * 0.5 + 0.05], -1)
+    boxes = boxes.expand(nq, bs, 4, 4).contiguous()
+    mask = torch.zeros(bs, S, dtype=torch.bool, device=dev)
+    cur = 0
+    for h, w in shapes:  # image 1: the right 40 % of every level is padding
+        mm = torch.zeros(h, w, dtype=torch.bool)
+        mm[:, int(0.6 * w):] = True
+        mask[1, cur:cur + h * w] = mm.reshape(-1).to(dev)
+        cur += h * w
+    go = torch.randn(nq, bs, 256, device=dev)
+
+    x = tgt.clone().requires_grad_(True)
+    mem = memory.clone().requires_grad_(True)
+    out = layer(x, qpos, boxes, mem, mask, starts, shp)
+    out.backward(go)
+    got_params = {k: p.grad.cpu() for k, p in layer.named_parameters()}
+
+    cpu = copy.deepcopy(layer).cpu()
+    cpu.zero_grad()
+    a = cpu.cross_attn
+    xs = tgt.detach().cpu().requires_grad_(True)
+    ms = memory.detach().cpu().requires_grad_(True)
+    qp, bx = qpos.cpu(), boxes.cpu()
+    q = k = xs + qp                                                            # :968
+    y = cpu.norm2(xs + cpu.self_attn(q, k, xs)[0])                             # :969-971
+    query = (y + qp).transpose(0, 1)                                           # :998
+    ref = bx.transpose(0, 1)
+    value = a.value_proj(ms.transpose(0, 1)).masked_fill(mask.cpu()[..., None], 0.0).view(bs, S, 8, 32)
+    off = a.sampling_offsets(query).view(bs, nq, 8, 4, 4, 2)
+    w = torch.softmax(a.attention_weights(query).view(bs, nq, 8, 16), -1).view(bs, nq, 8, 4, 4)
+    loc = ref[:, :, None, :, None, :2] + off / 4 * ref[:, :, None, :, None, 2:] * 0.5   # ms_deform_attn.py:106-108
+    y2 = a.output_proj(core_pytorch(value, shapes, loc, w)).transpose(0, 1)
+    y = cpu.norm1(y + y2)                                                      # :1002-1003
+    y = cpu.norm3(y + cpu.linear2(F.relu(cpu.linear1(y))))                     # :941-945
+    y.backward(go.cpu())
+    assert rel_err(out.detach().cpu(), y.detach()) < 1e-5
+    assert rel_err(x.grad.cpu(), xs.grad) < 1e-4
+    assert rel_err(mem.grad.cpu(), ms.grad) < 1e-4
+    for kname, p in cpu.named_parameters():
+        assert rel_err(got_params[kname], p.grad) < 2e-4, kname

@@ -189,3 +189,16 @@ def test_add_layer_norm_host_side_selection_and_oracle_expression():
     assert lib.msda_add_layernorm_f32(None, None, None, None, None, 10, 96, 1e-5, None, None, None) == 2  # UNSUPPORTED
     assert b"multiple of 128" in lib.msda_last_error()
     assert lib.msda_add_layernorm_f32(None, None, None, None, None, 0, 256, 1e-5, None, None, None) == 0  # empty: nothing to do
+
+
+def test_decoder_layer_parameter_names_follow_the_reference_layer():
+    """deformable_transformer.py:896-917: cross_attn / norm1 / self_attn / norm2 / linear1 / linear2 / norm3 (dropouts
+    have no parameters), so a reference decoder-layer state dict loads."""
+    from richsem_b200.decoder_layer import DeformableDecoderLayer
+
+    names = {k for k, _ in DeformableDecoderLayer().named_parameters()}
+    want = {f"cross_attn.{m}.{p}" for m in ("sampling_offsets", "attention_weights", "value_proj", "output_proj")
+            for p in ("weight", "bias")}
+    want |= {"self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight", "self_attn.out_proj.bias"}
+    want |= {f"{m}.{p}" for m in ("norm1", "norm2", "norm3", "linear1", "linear2") for p in ("weight", "bias")}
+    assert names == want
