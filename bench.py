@@ -68,6 +68,7 @@ WORKLOADS = {
 }
 # what the default invocation appends to the headline line: key -> (workload, options)
 EXTRA = [
+    ("encoder6_graph", "encoder6", {"graph": True}),  # the headline step replayed from one CUDA graph (no events inside)
     ("decoder6", "decoder6", {}),
     ("decoder6_graph", "decoder6", {"graph": True}),
     ("encoder1_hr1333", "encoder1_hr1333", {}),
